@@ -1,0 +1,18 @@
+"""gaplac_b200 — B200 (sm_100a) backend for GaPLAC's GP marginal-likelihood / posterior hot path.
+
+The product is libgaplac_b200.so (C ABI in include/gaplac_b200.h, CUDA kernels in gaplac_b200/csrc/).
+This package is the host-side mirror of the reference's interface for that path: the formula language
+(formula.py), the AbstractGPs-facing calls (gp.py), and the ctypes binding that stands in for Julia's
+`ccall` (_lib.py).  There is no CPU fallback.
+"""
+from .formula import (Cat, Constant, GPComponent, GPOperation, Gaussian, KernelProgram, Linear, Noise, Op, OU, Slot,
+                      Spec, SqExp, formula, gp_spec, kernel, likelihood, make_gp, parse_formula, response, varnames)
+from .gp import GP, FiniteGP, PosteriorGP, default_context, logpdf, logpdf_batched, mean, mean_and_var, posterior, rand
+from ._lib import Context, GaplacError, PosDefException, Program
+
+__all__ = [
+    "Cat", "Constant", "GPComponent", "GPOperation", "Gaussian", "KernelProgram", "Linear", "Noise", "Op", "OU",
+    "Slot", "Spec", "SqExp", "formula", "gp_spec", "kernel", "likelihood", "make_gp", "parse_formula", "response",
+    "varnames", "GP", "FiniteGP", "PosteriorGP", "default_context", "logpdf", "logpdf_batched", "mean",
+    "mean_and_var", "posterior", "rand", "Context", "GaplacError", "PosDefException", "Program",
+]

@@ -1,0 +1,766 @@
+// C ABI of libgaplac_b200.so (include/gaplac_b200.h): contexts, workspace pool, launch orchestration.
+// No torch types, no C++ types across the boundary; every entry point returns a gpl_status.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/gaplac_b200.h"
+#include "kernels.h"
+#include "tile.cuh"
+
+using namespace gpl;
+
+namespace {
+
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+constexpr int PANEL = 4;        // tile columns per panel of the large-n factorisation
+constexpr int SMALL_MAX_N = 512;  // posterior fits up to this n run on the one-CTA fused kernel
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct gpl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::string err;
+    std::mutex mu;
+    int lml_variant = 0;
+    int chol_variant = 0;
+    bool attr_lml = false, attr_big = false, attr_pred = false;
+    // grow-only device buffers
+    DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
+};
+
+struct gpl_prog {
+    DevProgram dev;
+};
+
+struct gpl_post {
+    gpl_ctx *ctx = nullptr;
+    DevProgram prog;
+    int n = 0, d = 0, nt = 0, p = 0;
+    double *dX = nullptr, *dtheta = nullptr;
+    double *tiles = nullptr, *winv = nullptr, *alpha = nullptr;
+    double lml = 0.0;
+};
+
+namespace {
+
+int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, GPL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                            \
+    } while (0)
+
+int ensure(gpl_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return GPL_OK;
+    if (b.p) CU(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return GPL_OK;
+}
+
+template <typename T>
+T *ptr(DevBuf &b) {
+    return static_cast<T *>(b.p);
+}
+
+int check_prog_args(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, int p) {
+    if (!ctx || !prog) return fail(ctx, GPL_ERR_ARG, "null context or program");
+    if (n <= 0 || d <= 0) return fail(ctx, GPL_ERR_ARG, "n=%d d=%d must be positive", n, d);
+    if (d < prog->dev.n_cols) return fail(ctx, GPL_ERR_ARG, "program reads column %d but d=%d", prog->dev.n_cols - 1, d);
+    if (p < prog->dev.n_theta) return fail(ctx, GPL_ERR_ARG, "program uses %d hyperparameter slots but p=%d", prog->dev.n_theta, p);
+    if (p > GPL_MAX_THETA) return fail(ctx, GPL_ERR_LIMIT, "p=%d exceeds %d", p, GPL_MAX_THETA);
+    return GPL_OK;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------------------
+int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched, const double *dY,
+               int y_batched, const double *dTheta, int p, const double *dsigma2, int sigma2_batched, double jitter,
+               int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
+               double *keep_ws, double *keep_vec, cudaStream_t st) {
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    const long long tiles_per_cta = ntri + nt + (want_grad ? ntri : 0);
+    const size_t smem = lml_smem_bytes();
+    bool &attr_set = ctx->attr_lml;
+    if (!attr_set) {
+        CU(ctx, cudaFuncSetAttribute(lml_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int occ = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_kernel, NTHREADS, smem));
+    if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "lml kernel does not fit on an SM (smem %zu)", smem);
+    int grid = ctx->sm_count * occ;
+    if (grid > B) grid = B;
+    LmlParams prm;
+    prm.prog = prog;
+    prm.n = n;
+    prm.d = d;
+    prm.nt = nt;
+    prm.B = B;
+    prm.p = p;
+    prm.want_grad = want_grad;
+    prm.keep = keep;
+    prm.sigma2_stride = sigma2_batched ? 1 : 0;
+    prm.x_stride = x_batched ? (long long)n * d : 0;
+    prm.y_stride = y_batched ? n : 0;
+    prm.X = dX;
+    prm.Y = dY;
+    prm.Theta = dTheta;
+    prm.sigma2 = dsigma2;
+    prm.jitter = jitter;
+    prm.ws_stride = tiles_per_cta * TILE_ELEMS;
+    if (keep) {
+        prm.ws = keep_ws;
+        prm.vec = keep_vec;
+        grid = 1;
+    } else {
+        int rc = ensure(ctx, ctx->ws, (size_t)grid * prm.ws_stride * sizeof(double));
+        if (rc) return rc;
+        rc = ensure(ctx, ctx->vec, (size_t)grid * 2 * nt * TS * sizeof(double));
+        if (rc) return rc;
+        prm.ws = ptr<double>(ctx->ws);
+        prm.vec = ptr<double>(ctx->vec);
+    }
+    int rc = ensure(ctx, ctx->counter, sizeof(unsigned int));
+    if (rc) return rc;
+    prm.counter = ptr<unsigned int>(ctx->counter);
+    CU(ctx, cudaMemsetAsync(prm.counter, 0, sizeof(unsigned int), st));
+    prm.lml = dlml;
+    prm.dtheta = ddtheta;
+    prm.dy = ddy;
+    prm.info = dinfo;
+    lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return GPL_OK;
+}
+
+// large-n factorisation of tile-major `tiles` (in place).  y (padded, nt*64) optional: becomes z = L^-1 y.
+int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *dinfo, double *y, int nt,
+               cudaStream_t st) {
+    const size_t smem = big_smem_bytes();
+    bool &attr_set = ctx->attr_big;
+    if (!attr_set) {
+        CU(ctx, cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    CU(ctx, cudaMemsetAsync(dinfo, 0, sizeof(int), st));
+    BigParams prm;
+    prm.tiles = tiles;
+    prm.winv = winv;
+    prm.pivlog = pivlog;
+    prm.info = dinfo;
+    prm.y = y;
+    prm.nt = nt;
+    for (int k0 = 0; k0 < nt; k0 += PANEL) {
+        const int j1 = (k0 + PANEL < nt) ? k0 + PANEL : nt;
+        prm.k0 = k0;
+        prm.j1 = j1;
+        for (int j = k0; j < j1; ++j) {
+            prm.j = j;
+            big_diag_kernel<<<1, NTHREADS, smem, st>>>(prm);
+            ctx->launches++;
+            if (j + 1 < nt) {
+                big_col_kernel<<<nt - j - 1, NTHREADS, smem, st>>>(prm);
+                ctx->launches++;
+            }
+        }
+        if (j1 < nt) {
+            const long long ntrail = tri_index(nt - j1, 0);
+            big_trail_kernel<<<(unsigned)ntrail, NTHREADS, smem, st>>>(prm);
+            ctx->launches++;
+        }
+    }
+    CU(ctx, cudaGetLastError());
+    return GPL_OK;
+}
+
+int launch_cov(gpl_ctx *ctx, const DevProgram &prog, int na, int nb, int d, int p, int same, const double *dXa,
+               const double *dXb, const double *dtheta, double diag_add, double *dK, cudaStream_t st) {
+    CovParams prm;
+    prm.prog = prog;
+    prm.na = na;
+    prm.nb = nb;
+    prm.d = d;
+    prm.p = p;
+    prm.same = same;
+    prm.Xa = dXa;
+    prm.Xb = dXb;
+    prm.theta = dtheta;
+    prm.diag_add = diag_add;
+    prm.K = dK;
+    dim3 grid((na + TS - 1) / TS, (nb + TS - 1) / TS);
+    cov_dense_kernel<<<grid, NTHREADS, 0, st>>>(prm);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return GPL_OK;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int gpl_abi_version(void) { return GPL_ABI_VERSION; }
+
+const char *gpl_last_error(gpl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int gpl_init(int device, gpl_ctx **out) {
+    if (!out) return fail(nullptr, GPL_ERR_ARG, "gpl_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, GPL_ERR_CUDA, "gpl_init: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(nullptr, GPL_ERR_ARG, "gpl_init: device %d out of range (%d devices)", device, count);
+    gpl_ctx *ctx = new (std::nothrow) gpl_ctx();
+    if (!ctx) return fail(nullptr, GPL_ERR_ARG, "gpl_init: out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, GPL_ERR_CUDA, "gpl_init: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, GPL_ERR_CUDA, "gpl_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device);
+    snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+    *out = ctx;
+    return GPL_OK;
+}
+
+int gpl_destroy(gpl_ctx *ctx) {
+    if (!ctx) return GPL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+                      &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
+                      &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GPL_OK;
+}
+
+uint64_t gpl_launch_count(gpl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key) return fail(ctx, GPL_ERR_ARG, "gpl_set_option: null argument");
+    if (!strcmp(key, "lml_variant")) ctx->lml_variant = value;
+    else if (!strcmp(key, "chol_variant")) ctx->chol_variant = value;
+    else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
+    return GPL_OK;
+}
+
+int gpl_device_info(gpl_ctx *ctx, char *name, int len, int *sm_count, int *clock_khz) {
+    if (!ctx) return fail(ctx, GPL_ERR_ARG, "null context");
+    if (name && len > 0) snprintf(name, len, "%s", ctx->name);
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    return GPL_OK;
+}
+
+// ---- program ---------------------------------------------------------------------------------------------------
+int gpl_program_create(gpl_ctx *ctx, const gpl_op *ops, int n_ops, gpl_prog **out) {
+    if (!out) return fail(ctx, GPL_ERR_ARG, "gpl_program_create: out is NULL");
+    *out = nullptr;
+    gpl_prog *p = new (std::nothrow) gpl_prog();
+    if (!p) return fail(ctx, GPL_ERR_ARG, "out of host memory");
+    char msg[192];
+    int rc = compile_program(ops, n_ops, &p->dev, msg);
+    if (rc) {
+        delete p;
+        return fail(ctx, rc, "%s", msg);
+    }
+    *out = p;
+    return GPL_OK;
+}
+int gpl_program_destroy(gpl_prog *prog) {
+    delete prog;
+    return GPL_OK;
+}
+int gpl_program_n_theta(const gpl_prog *prog) { return prog ? prog->dev.n_theta : GPL_ERR_ARG; }
+int gpl_program_n_cols(const gpl_prog *prog) { return prog ? prog->dev.n_cols : GPL_ERR_ARG; }
+
+// ---- covariance ------------------------------------------------------------------------------------------------
+int gpl_cov_dev(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *dX, const double *dtheta, int p,
+                double sigma2, double jitter, double *dK, void *stream) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!dX || !dK || (p > 0 && !dtheta)) return fail(ctx, GPL_ERR_ARG, "gpl_cov_dev: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return launch_cov(ctx, prog->dev, n, n, d, p, 1, dX, dX, dtheta, sigma2 + jitter, dK, (cudaStream_t)stream);
+}
+
+int gpl_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,
+            double sigma2, double jitter, double *K) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!X || !K || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_cov: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bTheta, (size_t)(p + 1) * 8)) ||
+        (rc = ensure(ctx, ctx->bK, (size_t)n * n * 8)))
+        return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, theta, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_cov(ctx, prog->dev, n, n, d, p, 1, ptr<double>(ctx->bX), ptr<double>(ctx->bX), ptr<double>(ctx->bTheta),
+                    sigma2 + jitter, ptr<double>(ctx->bK), st);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(K, ctx->bK.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+int gpl_cross_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int m, int d, const double *X, const double *Xs,
+                  const double *theta, int p, double *Ks) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (m <= 0 || !X || !Xs || !Ks || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_cross_cov: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bXs, (size_t)m * d * 8)) ||
+        (rc = ensure(ctx, ctx->bTheta, (size_t)(p + 1) * 8)) || (rc = ensure(ctx, ctx->bK, (size_t)n * m * 8)))
+        return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bXs.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, theta, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_cov(ctx, prog->dev, n, m, d, p, 0, ptr<double>(ctx->bX), ptr<double>(ctx->bXs), ptr<double>(ctx->bTheta),
+                    0.0, ptr<double>(ctx->bK), st);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(Ks, ctx->bK.p, (size_t)n * m * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+// ---- batched lml -----------------------------------------------------------------------------------------------
+int gpl_lml_batched_dev(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *dX, int x_batched,
+                        const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
+                        int sigma2_batched, double jitter, int B, double *dlml, double *ddtheta, double *ddy,
+                        int *dinfo, void *stream) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (B <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: B=%d", B);
+    if (!dX || !dY || !dsigma2 || !dlml || (p > 0 && !dTheta)) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int want_grad = ddtheta != nullptr;
+    return launch_lml(ctx, prog->dev, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
+                      dlml, ddtheta, ddy, dinfo, want_grad, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, int x_batched, const double *Y,
+                    int y_batched, const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter,
+                    int B, double *lml, double *dtheta, double *dy, int *info) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (B <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: B=%d", B);
+    if (!X || !Y || !sigma2 || !lml || (p > 0 && !Theta)) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: null pointer");
+    if (dy && !dtheta && p > 0) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: dy requires dtheta");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t xb = (size_t)n * d * (x_batched ? B : 1) * 8, yb = (size_t)n * (y_batched ? B : 1) * 8;
+    const size_t tb = (size_t)(p > 0 ? p : 1) * B * 8, sb = (size_t)(sigma2_batched ? B : 1) * 8;
+    if ((rc = ensure(ctx, ctx->bX, xb)) || (rc = ensure(ctx, ctx->bY, yb)) || (rc = ensure(ctx, ctx->bTheta, tb)) ||
+        (rc = ensure(ctx, ctx->bSigma, sb)) || (rc = ensure(ctx, ctx->bLml, (size_t)B * 8)) ||
+        (rc = ensure(ctx, ctx->bInfo, (size_t)B * 4)))
+        return rc;
+    const bool grad = dtheta != nullptr || dy != nullptr;
+    if (grad && ((rc = ensure(ctx, ctx->bDtheta, tb)) || (rc = ensure(ctx, ctx->bDy, (size_t)n * B * 8)))) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, xb, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bY.p, Y, yb, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, Theta, (size_t)p * B * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bSigma.p, sigma2, sb, cudaMemcpyHostToDevice, st));
+    rc = launch_lml(ctx, prog->dev, n, d, ptr<double>(ctx->bX), x_batched, ptr<double>(ctx->bY), y_batched,
+                    ptr<double>(ctx->bTheta), p, ptr<double>(ctx->bSigma), sigma2_batched, jitter, B, ptr<double>(ctx->bLml),
+                    grad ? ptr<double>(ctx->bDtheta) : nullptr, grad ? ptr<double>(ctx->bDy) : nullptr,
+                    ptr<int>(ctx->bInfo), grad ? 1 : 0, 0, nullptr, nullptr, st);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(lml, ctx->bLml.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (info) CU(ctx, cudaMemcpyAsync(info, ctx->bInfo.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (dtheta && p > 0) CU(ctx, cudaMemcpyAsync(dtheta, ctx->bDtheta.p, (size_t)p * B * 8, cudaMemcpyDeviceToHost, st));
+    if (dy) CU(ctx, cudaMemcpyAsync(dy, ctx->bDy.p, (size_t)n * B * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+// ---- posterior ---------------------------------------------------------------------------------------------------
+int gpl_posterior_free(gpl_post *post) {
+    if (!post) return GPL_OK;
+    if (post->ctx) cudaSetDevice(post->ctx->device);
+    cudaFree(post->dX);
+    cudaFree(post->dtheta);
+    cudaFree(post->tiles);
+    cudaFree(post->winv);
+    cudaFree(post->alpha);
+    delete post;
+    return GPL_OK;
+}
+
+static int posterior_fit_impl(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                              const double *theta, int p, double sigma2, double jitter, gpl_post *post) {
+    cudaStream_t st = ctx->stream;
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    post->ctx = ctx;
+    post->prog = prog->dev;
+    post->n = n;
+    post->d = d;
+    post->nt = nt;
+    post->p = p;
+    int rc;
+    CU(ctx, cudaMalloc(&post->dX, (size_t)n * d * 8));
+    CU(ctx, cudaMalloc(&post->dtheta, (size_t)(p + 1) * 8));
+    // tiles and the diagonal inverses are one allocation-compatible layout with the fused kernel's workspace:
+    // [ntri L tiles][nt W tiles]
+    CU(ctx, cudaMalloc(&post->tiles, (size_t)(ntri + nt) * TILE_BYTES));
+    post->winv = nullptr;
+    CU(ctx, cudaMalloc(&post->alpha, (size_t)2 * nt * TS * 8));  // [z | alpha]
+    CU(ctx, cudaMemcpyAsync(post->dX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(post->dtheta, theta, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+    double *winv = post->tiles + ntri * TILE_ELEMS;
+    double *zvec = post->alpha, *avec = post->alpha + (size_t)nt * TS;
+    if ((rc = ensure(ctx, ctx->bMisc, 64 + (size_t)nt * TS * 8))) return rc;
+    double *dres = ptr<double>(ctx->bMisc);               // [0]=lml or logdet, [1]=quad
+    int *dinfo = reinterpret_cast<int *>(dres + 4);
+    double *pivlog = dres + 8;
+    if ((rc = ensure(ctx, ctx->bY, (size_t)nt * TS * 8)) || (rc = ensure(ctx, ctx->bSigma, 8))) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->bY.p, 0, (size_t)nt * TS * 8, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bY.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    double h_lml = 0.0;
+    int h_info = 0;
+    if (n <= SMALL_MAX_N && ctx->chol_variant == 0) {
+        CU(ctx, cudaMemcpyAsync(ctx->bSigma.p, &sigma2, 8, cudaMemcpyHostToDevice, st));
+        rc = launch_lml(ctx, prog->dev, n, d, post->dX, 0, ptr<double>(ctx->bY), 0, post->dtheta, p, ptr<double>(ctx->bSigma),
+                        0, jitter, 1, dres, nullptr, nullptr, dinfo, 0, 1, post->tiles, post->alpha, st);
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(&h_lml, dres, 8, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(&h_info, dinfo, 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    } else {
+        CovTilesParams cp;
+        cp.prog = prog->dev;
+        cp.n = n;
+        cp.nt = nt;
+        cp.d = d;
+        cp.p = p;
+        cp.X = post->dX;
+        cp.theta = post->dtheta;
+        cp.diag_add = sigma2 + jitter;
+        cp.tiles = post->tiles;
+        cov_tiles_kernel<<<(unsigned)ntri, NTHREADS, 0, st>>>(cp);
+        ctx->launches++;
+        CU(ctx, cudaMemcpyAsync(zvec, ctx->bY.p, (size_t)nt * TS * 8, cudaMemcpyDeviceToDevice, st));
+        if ((rc = big_factor(ctx, post->tiles, winv, pivlog, dinfo, zvec, nt, st))) return rc;
+        big_reduce_kernel<<<1, NTHREADS, 0, st>>>(pivlog, zvec, nt * TS, dres);
+        ctx->launches++;
+        // backward substitution: r starts as a copy of z (kept), alpha written block by block
+        if ((rc = ensure(ctx, ctx->bDy, (size_t)nt * TS * 8))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->bDy.p, zvec, (size_t)nt * TS * 8, cudaMemcpyDeviceToDevice, st));
+        for (int i = nt - 1; i >= 0; --i) {
+            big_backward_kernel<<<i + 1, NTHREADS, 0, st>>>(post->tiles, winv, i, ptr<double>(ctx->bDy), avec);
+            ctx->launches++;
+        }
+        CU(ctx, cudaGetLastError());
+        double h_res[2];
+        CU(ctx, cudaMemcpyAsync(h_res, dres, 16, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(&h_info, dinfo, 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        h_lml = -0.5 * ((double)n * LOG2PI + h_res[0] + h_res[1]);
+    }
+    if (h_info != 0)
+        return fail(ctx, GPL_ERR_NOTPD, "covariance not positive definite: pivot %d (PosDefException(%d))", h_info, h_info);
+    post->lml = h_lml;
+    return GPL_OK;
+}
+
+int gpl_posterior_fit(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                      const double *theta, int p, double sigma2, double jitter, gpl_post **out) {
+    if (!out) return fail(ctx, GPL_ERR_ARG, "gpl_posterior_fit: out is NULL");
+    *out = nullptr;
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!X || !y || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_posterior_fit: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    gpl_post *post = new (std::nothrow) gpl_post();
+    if (!post) return fail(ctx, GPL_ERR_ARG, "out of host memory");
+    rc = posterior_fit_impl(ctx, prog, n, d, X, y, theta, p, sigma2, jitter, post);
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        gpl_posterior_free(post);
+        return rc;
+    }
+    *out = post;
+    return GPL_OK;
+}
+
+int gpl_posterior_logpdf(gpl_post *post, double *lml) {
+    if (!post || !lml) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_logpdf: null argument");
+    *lml = post->lml;
+    return GPL_OK;
+}
+
+int gpl_posterior_alpha(gpl_post *post, double *alpha) {
+    if (!post || !alpha) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_alpha: null argument");
+    gpl_ctx *ctx = post->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(alpha, post->alpha + (size_t)post->nt * TS, (size_t)post->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPL_OK;
+}
+
+int gpl_posterior_factor(gpl_post *post, double *U) {
+    if (!post || !U) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_factor: null argument");
+    gpl_ctx *ctx = post->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int n = post->n, nt = post->nt;
+    int rc = ensure(ctx, ctx->bK, (size_t)n * n * 8);
+    if (rc) return rc;
+    dim3 grid(nt, nt);
+    tiles_to_upper_kernel<<<grid, NTHREADS, 0, ctx->stream>>>(post->tiles, n, nt, ptr<double>(ctx->bK));
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(U, ctx->bK.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPL_OK;
+}
+
+int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean, double *var) {
+    if (!post || !Xs || !mean || m <= 0) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_mean_var: bad argument");
+    gpl_ctx *ctx = post->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nt = post->nt, d = post->d;
+    const size_t smem = predict_smem_bytes();
+    bool &attr_set = ctx->attr_pred;
+    if (!attr_set) {
+        CU(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int occ = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, predict_kernel, NTHREADS, smem));
+    if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "predict kernel does not fit on an SM");
+    const int nslab = (m + TS - 1) / TS;
+    int grid = ctx->sm_count * occ;
+    if (grid > nslab) grid = nslab;
+    int rc;
+    if ((rc = ensure(ctx, ctx->bXs, (size_t)m * d * 8)) || (rc = ensure(ctx, ctx->bMean, (size_t)m * 8)) ||
+        (rc = ensure(ctx, ctx->bVar, (size_t)m * 8)) || (rc = ensure(ctx, ctx->bWsV, (size_t)grid * nt * TILE_BYTES)))
+        return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bXs.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, st));
+    PredictParams prm;
+    prm.prog = post->prog;
+    prm.n = post->n;
+    prm.nt = nt;
+    prm.d = d;
+    prm.p = post->p;
+    prm.m = m;
+    prm.want_var = var != nullptr;
+    prm.X = post->dX;
+    prm.theta = post->dtheta;
+    prm.Xs = ptr<double>(ctx->bXs);
+    prm.tiles = post->tiles;
+    prm.winv = post->tiles + tri_index(nt, 0) * TILE_ELEMS;
+    prm.alpha = post->alpha + (size_t)nt * TS;
+    prm.wsV = ptr<double>(ctx->bWsV);
+    prm.mean = ptr<double>(ctx->bMean);
+    prm.var = ptr<double>(ctx->bVar);
+    predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(mean, ctx->bMean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (var) CU(ctx, cudaMemcpyAsync(var, ctx->bVar.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+// ---- sample --------------------------------------------------------------------------------------------------------
+int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,
+               double sigma2, double jitter, const double *Z, int S, double *out) {
+    if (!Z || !out || S <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_sample: bad argument");
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!X || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_sample: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    gpl_post *post = new (std::nothrow) gpl_post();
+    if (!post) return fail(ctx, GPL_ERR_ARG, "out of host memory");
+    double *zeros = new (std::nothrow) double[n]();
+    rc = zeros ? posterior_fit_impl(ctx, prog, n, d, X, zeros, theta, p, sigma2, jitter, post) : GPL_ERR_ARG;
+    delete[] zeros;
+    if (rc == GPL_OK) {
+        cudaStream_t st = ctx->stream;
+        rc = ensure(ctx, ctx->bK, (size_t)2 * n * S * 8);
+        if (rc == GPL_OK) {
+            double *dZ = ptr<double>(ctx->bK), *dOut = dZ + (size_t)n * S;
+            cudaError_t e = cudaMemcpyAsync(dZ, Z, (size_t)n * S * 8, cudaMemcpyHostToDevice, st);
+            sample_kernel<<<post->nt, NTHREADS, 0, st>>>(post->tiles, post->nt, n, dZ, S, dOut);
+            ctx->launches++;
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut, (size_t)n * S * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(ctx, GPL_ERR_CUDA, "gpl_sample: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    gpl_posterior_free(post);
+    return rc;
+}
+
+// ---- large-n ---------------------------------------------------------------------------------------------------------
+int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo, void *stream) {
+    if (!ctx || !dA || !dlogdet || !dinfo || n <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_chol_logdet_dev: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    int rc;
+    if ((rc = ensure(ctx, ctx->ws, (size_t)(ntri + nt) * TILE_BYTES)) || (rc = ensure(ctx, ctx->bMisc, 64 + (size_t)nt * TS * 8)))
+        return rc;
+    double *tiles = ptr<double>(ctx->ws), *winv = tiles + ntri * TILE_ELEMS;
+    double *dres = ptr<double>(ctx->bMisc), *pivlog = dres + 8;
+    dense_to_tiles_kernel<<<(unsigned)ntri, NTHREADS, 0, st>>>(dA, n, nt, tiles);
+    ctx->launches++;
+    if ((rc = big_factor(ctx, tiles, winv, pivlog, dinfo, nullptr, nt, st))) return rc;
+    big_reduce_kernel<<<1, NTHREADS, 0, st>>>(pivlog, nullptr, nt * TS, dres);
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(dlogdet, dres, 8, cudaMemcpyDeviceToDevice, st));
+    if (want_factor) {
+        dim3 grid(nt, nt);
+        tiles_to_upper_kernel<<<grid, NTHREADS, 0, st>>>(tiles, n, nt, dA);
+        ctx->launches++;
+    }
+    CU(ctx, cudaGetLastError());
+    return GPL_OK;
+}
+
+int gpl_chol_logdet(gpl_ctx *ctx, int n, double *A, int want_factor, double *logdet, int *info) {
+    if (!ctx || !A || !logdet || n <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_chol_logdet: bad argument");
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(ctx, cudaSetDevice(ctx->device));
+        if ((rc = ensure(ctx, ctx->bK, (size_t)n * n * 8)) || (rc = ensure(ctx, ctx->bLml, 16)) ||
+            (rc = ensure(ctx, ctx->bInfo, 4)))
+            return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->bK.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = gpl_chol_logdet_dev(ctx, n, ptr<double>(ctx->bK), want_factor, ptr<double>(ctx->bLml), ptr<int>(ctx->bInfo),
+                             ctx->stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int h_info = 0;
+    CU(ctx, cudaMemcpyAsync(logdet, ctx->bLml.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&h_info, ctx->bInfo.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_factor) CU(ctx, cudaMemcpyAsync(A, ctx->bK.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info) *info = h_info;
+    if (h_info) *logdet = NAN;
+    return GPL_OK;
+}
+
+int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                  const double *theta, int p, double sigma2, double jitter, double *lml, double *logdet, int *info) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!X || !y || !lml || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_lml_large: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    if ((rc = ensure(ctx, ctx->ws, (size_t)(ntri + nt) * TILE_BYTES)) || (rc = ensure(ctx, ctx->bMisc, 64 + (size_t)nt * TS * 8)) ||
+        (rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bTheta, (size_t)(p + 1) * 8)) ||
+        (rc = ensure(ctx, ctx->bY, (size_t)nt * TS * 8)))
+        return rc;
+    double *tiles = ptr<double>(ctx->ws), *winv = tiles + ntri * TILE_ELEMS;
+    double *dres = ptr<double>(ctx->bMisc), *pivlog = dres + 8;
+    int *dinfo = reinterpret_cast<int *>(dres + 4);
+    CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, theta, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemsetAsync(ctx->bY.p, 0, (size_t)nt * TS * 8, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bY.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CovTilesParams cp;
+    cp.prog = prog->dev;
+    cp.n = n;
+    cp.nt = nt;
+    cp.d = d;
+    cp.p = p;
+    cp.X = ptr<double>(ctx->bX);
+    cp.theta = ptr<double>(ctx->bTheta);
+    cp.diag_add = sigma2 + jitter;
+    cp.tiles = tiles;
+    cov_tiles_kernel<<<(unsigned)ntri, NTHREADS, 0, st>>>(cp);
+    ctx->launches++;
+    if ((rc = big_factor(ctx, tiles, winv, pivlog, dinfo, ptr<double>(ctx->bY), nt, st))) return rc;
+    big_reduce_kernel<<<1, NTHREADS, 0, st>>>(pivlog, ptr<double>(ctx->bY), nt * TS, dres);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    double h_res[2];
+    int h_info = 0;
+    CU(ctx, cudaMemcpyAsync(h_res, dres, 16, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(&h_info, dinfo, 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (info) *info = h_info;
+    if (logdet) *logdet = h_info ? NAN : h_res[0];
+    *lml = h_info ? -INFINITY : -0.5 * ((double)n * LOG2PI + h_res[0] + h_res[1]);
+    return GPL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// Single large-n model: blocked Cholesky over the whole GPU on tile-major storage, with the forward solve
+// fused into the panel kernels (BASELINE config 5: n = 8192; also posterior fits with n > 1024).
+//
+// Replaces cholesky(Symmetric(K_y)) -> dpotrf('U') + U' \ y -> dtrtrs + logdet [upstream LinearAlgebra /
+// OpenBLAS via AbstractGPs logpdf / posterior]; call sites CLI/src/select.jl:49-52, src/plotting.jl:8.
+//
+// Two-level blocking.  A panel is PANEL tile columns (256 matrix columns).  Inside a panel the tile columns are
+// factored left-looking (big_diag_kernel: 1 CTA; big_col_kernel: one CTA per tile below the diagonal); after
+// a panel, big_trail_kernel applies its rank-256 update to every remaining tile (one CTA per tile, K = 256 so
+// the trailing matrix moves through HBM once per panel, not once per tile column).
+#include "kernels.h"
+#include "tile.cuh"
+
+namespace gpl {
+
+namespace {
+struct __align__(16) BigSmem {
+    double A[TILE_ELEMS];
+    double Bt[TILE_ELEMS];
+    double W[TILE_ELEMS];
+    double colbuf[2 * TS];
+    double rowbuf[2 * TS];
+    double pivbuf[TS];
+    double ybuf[TS];
+};
+
+__device__ __forceinline__ void acc_from_smem(double (&acc)[4][4], const double *T, TMap tm) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const double *p = T + col_of(tm.cb, cc) * TS + tm.m0;
+        const double2 v01 = *reinterpret_cast<const double2 *>(p);
+        const double2 v23 = *reinterpret_cast<const double2 *>(p + 2);
+        acc[0][cc] = v01.x;
+        acc[1][cc] = v01.y;
+        acc[2][cc] = v23.x;
+        acc[3][cc] = v23.y;
+    }
+}
+}  // namespace
+
+size_t big_smem_bytes() { return sizeof(BigSmem); }
+
+__global__ void __launch_bounds__(NTHREADS) dense_to_tiles_kernel(const double *__restrict__ A, int n, int nt,
+                                                                  double *__restrict__ tiles) {
+    const long long t = blockIdx.x;
+    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (tri_index(i + 1, 0) <= t) ++i;
+    while (tri_index(i, 0) > t) --i;
+    const int j = (int)(t - tri_index(i, 0));
+    double *tile = tiles + t * TILE_ELEMS;
+    for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
+        const int r = e & (TS - 1), c = e >> 6;
+        int gr = i * TS + r, gc = j * TS + c;
+        double v;
+        if (gr >= n || gc >= n) {
+            v = (gr == gc) ? 1.0 : 0.0;
+        } else {
+            if (gr < gc) {  // upper part of a diagonal tile: mirror the lower triangle
+                const int tmp = gr;
+                gr = gc;
+                gc = tmp;
+            }
+            v = A[(size_t)gc * n + gr];
+        }
+        tile[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) tiles_to_upper_kernel(const double *__restrict__ tiles, int n, int nt,
+                                                                  double *__restrict__ U) {
+    __shared__ double T[TS][TS + 1];
+    const int ti = blockIdx.x, tj = blockIdx.y;  // block (ti, tj) of U: rows ti*64.., cols tj*64..
+    if (ti <= tj) {
+        const double *tile = tiles + tri_index(tj, ti) * TILE_ELEMS;  // L block (tj, ti)
+        for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) T[e >> 6][e & (TS - 1)] = tile[e];  // T[c][r]
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
+        const int a = e & (TS - 1), b = e >> 6;  // U local (a, b): row a, column b
+        const int ga = ti * TS + a, gb = tj * TS + b;
+        if (ga >= n || gb >= n) continue;
+        // U(a, b) = L(b, a): L tile element (row b, col a) = T[a][b]
+        U[(size_t)gb * n + ga] = (ti <= tj && ga <= gb) ? T[a][b] : 0.0;
+    }
+}
+
+// tile (j, j): left-looking update with the panel's earlier columns, Cholesky + inverse, forward-solve block
+__global__ void __launch_bounds__(NTHREADS) big_diag_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, j = prm.j;
+    const TMap tm = thread_map(tid);
+    double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
+    tile_load_async(sm.A, Tjj, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][4];
+    acc_from_smem(acc, sm.A, tm);
+    for (int k = prm.k0; k < j; ++k) {
+        __syncthreads();
+        tile_load_async(sm.A, prm.tiles + tri_index(j, k) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_gemm<true>(acc, sm.A, sm.A, tm, 0, TS);
+    }
+    __syncthreads();
+    double w[4][4];
+    const int fail = tile_potrf_inv(acc, w, tm, sm.colbuf, sm.rowbuf, sm.pivbuf, tid);
+    if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
+    acc_to_smem(sm.A, acc, tm);
+    acc_to_smem(sm.W, w, tm);
+    __syncthreads();
+    tile_store(Tjj, sm.A, tid);
+    tile_store(prm.winv + (size_t)j * TILE_ELEMS, sm.W, tid);
+    if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
+    if (prm.y && tid < TS) {
+        // z_j = W_jj y_j (y_j already carries the updates of all earlier tile columns)
+        const double *yj = prm.y + j * TS;
+        double s = 0.0;
+        for (int c = 0; c <= tid; ++c) s = fma(sm.W[c * TS + tid], yj[c], s);
+        sm.ybuf[tid] = s;
+    }
+    __syncthreads();
+    if (prm.y && tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+}
+
+// tiles (i, j), i > j: left-looking update inside the panel, then L_ij = T_ij W_jj', then y_i -= L_ij z_j
+__global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x;
+    const TMap tm = thread_map(tid);
+    double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
+    tile_load_async(sm.A, Tij, tid);
+    tile_load_async(sm.W, prm.winv + (size_t)j * TILE_ELEMS, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][4];
+    acc_from_smem(acc, sm.A, tm);
+    for (int k = prm.k0; k < j; ++k) {
+        __syncthreads();
+        tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+        tile_load_async(sm.Bt, prm.tiles + tri_index(j, k) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_gemm<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+    }
+    __syncthreads();
+    acc_to_smem(sm.A, acc, tm);
+    __syncthreads();
+    double x[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[r][c] = 0.0;
+    const int kmax = ((tid >> 5) & 1) * 32 + 32;
+    tile_gemm<false>(x, sm.A, sm.W, tm, 0, kmax);
+    __syncthreads();
+    acc_to_smem(sm.A, x, tm);
+    __syncthreads();
+    tile_store(Tij, sm.A, tid);
+    if (prm.y && tid < TS) {
+        const double *zj = prm.y + j * TS;
+        double s = 0.0;
+#pragma unroll 8
+        for (int kk = 0; kk < TS; ++kk) s = fma(sm.A[kk * TS + tid], zj[kk], s);
+        prm.y[i * TS + tid] -= s;
+    }
+}
+
+// trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'
+__global__ void __launch_bounds__(NTHREADS) big_trail_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const TMap tm = thread_map(tid);
+    const long long t = blockIdx.x;
+    int ii = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (tri_index(ii + 1, 0) <= t) ++ii;
+    while (tri_index(ii, 0) > t) --ii;
+    const int ll = (int)(t - tri_index(ii, 0));
+    const int i = prm.j1 + ii, l = prm.j1 + ll;
+    double *Til = prm.tiles + tri_index(i, l) * TILE_ELEMS;
+    tile_load_async(sm.W, Til, tid);
+    cp_async_commit();
+    double acc[4][4];
+    bool first = true;
+    for (int k = prm.k0; k < prm.j1; ++k) {
+        __syncthreads();
+        tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+        if (i != l) tile_load_async(sm.Bt, prm.tiles + tri_index(l, k) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        if (first) {
+            acc_from_smem(acc, sm.W, tm);
+            first = false;
+        }
+        tile_gemm<true>(acc, sm.A, (i == l) ? sm.A : sm.Bt, tm, 0, TS);
+    }
+    __syncthreads();
+    acc_to_smem(sm.A, acc, tm);
+    __syncthreads();
+    tile_store(Til, sm.A, tid);
+}
+
+// backward substitution, one launch per tile row i (descending), grid = i + 1: every CTA recomputes
+// alpha_i = W_ii' r_i (r_i is final and read-only in this launch), CTA j < i applies r_j -= L_ij' alpha_i,
+// CTA j == i writes alpha_i to the output vector.
+__global__ void __launch_bounds__(NTHREADS) big_backward_kernel(const double *tiles, const double *winv, int i,
+                                                                double *r, double *alpha) {
+    __shared__ __align__(16) double T[TILE_ELEMS];
+    __shared__ double v[TS], a[TS];
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x;  // 0..i
+    tile_load_async(T, winv + (size_t)i * TILE_ELEMS, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    if (tid < TS) v[tid] = r[i * TS + tid];
+    __syncthreads();
+    if (tid < TS) {
+        double s = 0.0;
+        for (int t = 0; t < TS; ++t) {
+            const int m = (tid + t) & (TS - 1);
+            s = fma(T[tid * TS + m], v[m], s);
+        }
+        a[tid] = s;
+    }
+    __syncthreads();
+    if (j == i) {
+        if (tid < TS) alpha[i * TS + tid] = a[tid];
+        return;
+    }
+    tile_load_async(T, tiles + tri_index(i, j) * TILE_ELEMS, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tid < TS) {
+        double s = 0.0;
+        for (int t = 0; t < TS; ++t) {
+            const int m = (tid + t) & (TS - 1);
+            s = fma(T[tid * TS + m], a[m], s);
+        }
+        r[j * TS + tid] -= s;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) big_reduce_kernel(const double *pivlog, const double *z, int len,
+                                                              double *out) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    double ld = 0.0, q = 0.0;
+    for (int t = tid; t < len; t += NTHREADS) {
+        ld += pivlog[t];
+        if (z) q = fma(z[t], z[t], q);
+    }
+    ld = block_sum(ld, red, tid);
+    q = block_sum(q, red, tid);
+    if (tid == 0) {
+        out[0] = ld;
+        out[1] = q;
+    }
+}
+
+}  // namespace gpl

@@ -1,0 +1,95 @@
+// Kernel parameter blocks and host-side launchers (internal; the public surface is include/gaplac_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "program.h"
+
+namespace gpl {
+
+// ---- batched fused lml (lml_batched.cu) ---------------------------------------------------------------------
+struct LmlParams {
+    DevProgram prog;
+    int n, d, nt, B, p;
+    int want_grad, keep;
+    int sigma2_stride;
+    long long x_stride, y_stride;  // doubles between items (0 = shared)
+    const double *X, *Y, *Theta, *sigma2;
+    double jitter;
+    double *ws;            // per-CTA tile workspace
+    long long ws_stride;   // doubles
+    double *vec;           // per-CTA vectors: z and alpha, 2 * nt * 64 doubles
+    double *lml, *dtheta, *dy;
+    int *info;
+    unsigned int *counter;  // dynamic work distribution (NULL: item = blockIdx.x)
+};
+__global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);
+size_t lml_smem_bytes();
+
+// ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
+struct CovParams {
+    DevProgram prog;
+    int na, nb, d, p;
+    int same;  // 1: K(X,X) + diag_add I ; 0: cross-covariance K(Xa, Xb)
+    const double *Xa, *Xb, *theta;
+    double diag_add;
+    double *K;  // na x nb column-major
+};
+__global__ void cov_dense_kernel(const __grid_constant__ CovParams prm);
+
+// K_y of a program straight into the tile-major lower layout used by the large-n factorisation
+struct CovTilesParams {
+    DevProgram prog;
+    int n, nt, d, p;
+    const double *X, *theta;
+    double diag_add;
+    double *tiles;
+};
+__global__ void cov_tiles_kernel(const __grid_constant__ CovTilesParams prm);
+
+// ---- layout conversion (big.cu) -----------------------------------------------------------------------------------
+// dense column-major lower triangle (ld = n) -> tile-major lower, identity padding
+__global__ void dense_to_tiles_kernel(const double *__restrict__ A, int n, int nt, double *__restrict__ tiles);
+// tile-major lower factor L -> dense upper factor U = L' (zeros below the diagonal), column-major ld = n
+__global__ void tiles_to_upper_kernel(const double *__restrict__ tiles, int n, int nt, double *__restrict__ U);
+
+// ---- large-n blocked Cholesky on tile-major storage (big.cu) --------------------------------------------------------
+struct BigParams {
+    double *tiles;  // lower tiles, in place: A on entry, L on exit
+    double *winv;   // nt tiles: inverses of the diagonal tiles
+    double *pivlog; // nt * 64 doubles: log of the pivots
+    int *info;      // single int, first failing pivot (1-based) or 0
+    double *y;      // optional padded right-hand side (nt*64): y on entry, z = L^-1 y on exit; NULL to skip
+    int nt;
+    int j;          // current tile column
+    int k0;         // first tile column of the current panel (left-looking inside the panel)
+    int j1;         // trailing update: one past the last tile column of the finished panel
+};
+__global__ void big_diag_kernel(BigParams prm);   // 1 CTA
+__global__ void big_col_kernel(BigParams prm);    // nt - j - 1 CTAs
+__global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l >= j1)
+size_t big_smem_bytes();
+
+// backward substitution alpha = L^-T z, one launch per tile row i (descending), grid = i + 1 CTAs; r = z on entry
+// of the first launch and is updated in place, alpha receives the finished blocks
+__global__ void big_backward_kernel(const double *tiles, const double *winv, int i, double *r, double *alpha);
+// logdet = sum pivlog, quad = z'z -> out[0] = logdet, out[1] = quad
+__global__ void big_reduce_kernel(const double *pivlog, const double *z, int len, double *out);
+
+// ---- posterior prediction and sampling (predict.cu) ------------------------------------------------------------------
+struct PredictParams {
+    DevProgram prog;
+    int n, nt, d, p, m;
+    int want_var;
+    const double *X, *theta, *Xs;  // Xs: m x d column-major
+    const double *tiles, *winv, *alpha;
+    double *wsV;          // per-CTA workspace, nt tiles
+    double *mean, *var;
+};
+__global__ void predict_kernel(const __grid_constant__ PredictParams prm);
+size_t predict_smem_bytes();
+
+// out (n x S) = L Z
+__global__ void sample_kernel(const double *tiles, int nt, int n, const double *Z, int S, double *out);
+
+}  // namespace gpl

@@ -1,0 +1,207 @@
+// Device-side evaluation of the compiled kernel-program (program.h) on register blocks of matrix entries.
+//
+// Replaces kernelmatrix(k, RowVecs(X)) [upstream KernelFunctions 0.10.38] reached from the FiniteGP call
+// sites (CLI/src/mcmc.jl:35, CLI/src/select.jl:43,47, CLI/src/sample.jl:25, src/plotting.jl:6): leaves per
+// src/abstractgp_translations.jl:8-15 and src/gp_parts.jl:11-13.  Nothing is materialised per node: each
+// thread evaluates sum_t coef_t prod_f leaf_f for its own R x C block of entries, in registers.
+#pragma once
+#include "program.h"
+
+namespace gpl {
+
+// per-item scalars derived from theta once per CTA (shared memory)
+struct ItemScalars {
+    double a[GPL_MAX_FACTORS];   // SQEXP: -1/(2 l^2); OU: -1/l; LINEAR: c; PARAM: theta
+    double da[GPL_MAX_FACTORS];  // derivative scale: SQEXP 1/l^3 (dk = k d^2 / l^3); OU 1/l^2 (dk = k |d| / l^2)
+};
+
+__device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const double *__restrict__ theta,
+                                                     ItemScalars *S, int tid) {
+    if (tid < P.n_factors) {
+        const DevFactor f = P.f[tid];
+        double h = f.slot >= 0 ? theta[f.slot] : f.value;
+        double a = h, da = 1.0;
+        if (f.kind == F_SQEXP) {
+            a = -0.5 / (h * h);
+            da = 1.0 / (h * h * h);
+        } else if (f.kind == F_OU) {
+            a = -1.0 / h;
+            da = 1.0 / (h * h);
+        }
+        S->a[tid] = a;
+        S->da[tid] = da;
+    }
+}
+
+// leaf value for one pair; `same_idx` = the two row indices are the same observation (Noise only)
+__device__ __forceinline__ double leaf_value(int kind, double a, double xi, double xj, bool same_idx) {
+    switch (kind) {
+    case F_SQEXP: {
+        double d = xi - xj;
+        return exp(a * (d * d));
+    }
+    case F_OU:
+        return exp(a * fabs(xi - xj));
+    case F_LINEAR:
+        return fma(xi, xj, a);
+    case F_CAT:
+        return xi == xj ? 1.0 : 0.0;
+    case F_NOISE:
+        return same_idx ? 1.0 : 0.0;
+    default:  // F_PARAM
+        return a;
+    }
+}
+
+// d leaf / d (its own hyperparameter), given the leaf value k
+__device__ __forceinline__ double leaf_deriv(int kind, double da, double k, double xi, double xj) {
+    switch (kind) {
+    case F_SQEXP: {
+        double d = xi - xj;
+        return k * (d * d) * da;
+    }
+    case F_OU:
+        return k * fabs(xi - xj) * da;
+    case F_LINEAR:
+    case F_PARAM:
+        return 1.0;
+    default:
+        return 0.0;
+    }
+}
+
+// Evaluate the program on the block rows gi[0..R) x cols gj[0..C).
+//   Xa: column-major, leading dimension lda, na valid rows (row indices); Xb likewise for column indices.
+//   SAME: Xa and Xb are the same observation set (K(X,X)): Noise = [gi == gj], diag_add goes on gi == gj,
+//         and indices >= na are the identity padding of the tiled factorisation (1 on the diagonal, 0 off it).
+//   !SAME: cross-covariance K(X, X*): Noise = 0, out-of-range entries = 0.
+template <int R, int C, bool SAME>
+__device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
+                                           int lda, int na, const int (&gi)[R], const double *__restrict__ Xb, int ldb,
+                                           int nb, const int (&gj)[C], double diag_add, double (&out)[R][C]) {
+    int ci[R], cj[C];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ci[r] = gi[r] < na ? gi[r] : na - 1;
+#pragma unroll
+    for (int c = 0; c < C; ++c) cj[c] = gj[c] < nb ? gj[c] : nb - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[r][c] = 0.0;
+
+    for (int t = 0; t < P.n_terms; ++t) {
+        double prod[R][C];
+        const double coef = P.coef[t];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) prod[r][c] = coef;
+        for (int f = P.term_begin[t]; f < P.term_begin[t + 1]; ++f) {
+            const int kind = P.f[f].kind;
+            const double a = S.a[f];
+            if (kind == F_PARAM) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) prod[r][c] *= a;
+            } else if (kind == F_NOISE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) prod[r][c] = (SAME && gi[r] == gj[c]) ? prod[r][c] : 0.0;
+            } else {
+                const int col = P.f[f].col;
+                double xi[R], xj[C];
+#pragma unroll
+                for (int r = 0; r < R; ++r) xi[r] = Xa[(size_t)col * lda + ci[r]];
+#pragma unroll
+                for (int c = 0; c < C; ++c) xj[c] = Xb[(size_t)col * ldb + cj[c]];
+                if (kind == F_SQEXP) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            double d = xi[r] - xj[c];
+                            prod[r][c] *= exp(a * (d * d));
+                        }
+                } else if (kind == F_OU) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) prod[r][c] *= exp(a * fabs(xi[r] - xj[c]));
+                } else if (kind == F_LINEAR) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) prod[r][c] *= fma(xi[r], xj[c], a);
+                } else {  // F_CAT
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) prod[r][c] = (xi[r] == xj[c]) ? prod[r][c] : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[r][c] += prod[r][c];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const bool inr = gi[r] < na && gj[c] < nb;
+            if (SAME) {
+                if (gi[r] == gj[c]) out[r][c] = inr ? out[r][c] + diag_add : 1.0;
+                else if (!inr) out[r][c] = 0.0;
+            } else if (!inr) {
+                out[r][c] = 0.0;
+            }
+        }
+}
+
+// Contract a weight block w[r][c] with dK/dtheta_s for every slot s:  g[s] += sum_rc w[r][c] dK[r][c]/dtheta_s.
+// gsum: shared-memory accumulators (GPL_MAX_THETA doubles); one atomicAdd per (term, factor-with-slot, warp).
+template <int R, int C>
+__device__ __forceinline__ void contract_grad_block(const DevProgram &P, const ItemScalars &S,
+                                                    const double *__restrict__ X, int ldx, int n, const int (&gi)[R],
+                                                    const int (&gj)[C], const double (&w)[R][C], double *gsum) {
+    int ci[R], cj[C];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ci[r] = gi[r] < n ? gi[r] : n - 1;
+#pragma unroll
+    for (int c = 0; c < C; ++c) cj[c] = gj[c] < n ? gj[c] : n - 1;
+    for (int t = 0; t < P.n_terms; ++t) {
+        for (int f = P.term_begin[t]; f < P.term_begin[t + 1]; ++f) {
+            const int slot = P.f[f].slot;
+            if (slot < 0) continue;
+            double part = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (gi[r] >= n || gj[c] >= n) continue;
+                    double v = P.coef[t];
+                    const bool same = gi[r] == gj[c];
+                    for (int g = P.term_begin[t]; g < P.term_begin[t + 1]; ++g) {
+                        const DevFactor fg = P.f[g];
+                        double xi = 0.0, xj = 0.0;
+                        if (fg.kind <= F_CAT) {
+                            xi = X[(size_t)fg.col * ldx + ci[r]];
+                            xj = X[(size_t)fg.col * ldx + cj[c]];
+                        }
+                        double k = leaf_value(fg.kind, S.a[g], xi, xj, same);
+                        v *= (g == f) ? leaf_deriv(fg.kind, S.da[g], k, xi, xj) : k;
+                    }
+                    part = fma(w[r][c], v, part);
+                }
+            // warp reduction, then one shared-memory atomic per warp
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&gsum[slot], part);
+        }
+    }
+}
+
+}  // namespace gpl

@@ -1,0 +1,151 @@
+// Posterior mean / variance at test points, and prior sampling, from a factor resident in HBM.
+//
+// Replaces mean_and_var(PosteriorGP, X*) [upstream AbstractGPs 0.5.12] (call site src/plotting.jl:12):
+//   mean = K(X*, X) alpha ;  var = diag K(X*, X*) - colsumsq(U' \ K(X, X*))   (latent f; sigma2 not added back)
+// and rand(FiniteGP) = U' z (call site CLI/src/sample.jl:25).
+//
+// predict_kernel: each CTA owns slabs of 64 test points.  K* is generated tile by tile in registers (never
+// materialised), the triangular solve V = L^-1 K* is blocked on 64 x 64 tiles with the inverted diagonal
+// tiles (all GEMM), and the column sums of squares / the mean are accumulated on the fly.
+#include "kernels.h"
+#include "kfun.cuh"
+#include "tile.cuh"
+
+namespace gpl {
+
+namespace {
+struct __align__(16) PredSmem {
+    double A[TILE_ELEMS];
+    double Bt[TILE_ELEMS];
+    double part[16 * TS];  // per row-group partial column sums
+    ItemScalars sc;
+};
+}  // namespace
+
+size_t predict_smem_bytes() { return sizeof(PredSmem); }
+
+__global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_constant__ PredictParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PredSmem &sm = *reinterpret_cast<PredSmem *>(smem_raw);
+    const DevProgram &P = prm.prog;
+    const int tid = threadIdx.x;
+    const TMap tm = thread_map(tid);
+    const int n = prm.n, nt = prm.nt, m = prm.m;
+    const int rg = tm.m0 >> 2;  // row group 0..15
+    double *wsV = prm.wsV + (size_t)blockIdx.x * nt * TILE_ELEMS;
+    prepare_item_scalars(P, prm.theta, &sm.sc, tid);
+    __syncthreads();
+
+    const int nslab = (m + TS - 1) / TS;
+    for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
+        int gj[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gj[c] = s * TS + col_of(tm.cb, c);
+        double csq[4] = {0.0, 0.0, 0.0, 0.0}, cmean[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nt; ++i) {
+            int gi[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) gi[r] = i * TS + tm.m0 + r;
+            double acc[4][4];
+            eval_block<4, 4, false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double al = gi[r] < n ? prm.alpha[gi[r]] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cmean[c] = fma(acc[r][c], al, cmean[c]);
+            }
+            if (!prm.want_var) continue;
+            // acc -= sum_{k<i} L_ik V_k   (V_k stored transposed: element (kk, col) at kk*64 + col)
+            for (int k = 0; k < i; ++k) {
+                __syncthreads();
+                tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+                tile_load_async(sm.Bt, wsV + (size_t)k * TILE_ELEMS, tid);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                tile_gemm<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+            }
+            // V_i = W_ii acc  (W lower triangular: row m needs kk <= m)
+            __syncthreads();
+            tile_load_async(sm.A, prm.winv + (size_t)i * TILE_ELEMS, tid);
+            cp_async_commit();
+            acc_to_smem_t(sm.Bt, acc, tm);
+            cp_async_wait<0>();
+            __syncthreads();
+            double v[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[r][c] = 0.0;
+            const int kmax = ((tid >> 6) + 1) * 16;  // rows of this warp are < kmax
+            tile_gemm<false>(v, sm.A, sm.Bt, tm, 0, kmax);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) csq[c] = fma(v[r][c], v[r][c], csq[c]);
+            if (i + 1 < nt) {
+                __syncthreads();
+                acc_to_smem_t(sm.A, v, tm);
+                __syncthreads();
+                tile_store(wsV + (size_t)i * TILE_ELEMS, sm.A, tid);
+            }
+        }
+        // reduce the per-thread partials over the 16 row groups (deterministic order)
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm.part[rg * TS + col_of(tm.cb, c)] = cmean[c];
+        __syncthreads();
+        if (tid < TS && s * TS + tid < m) {
+            double sum = 0.0;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) sum += sm.part[g * TS + tid];
+            prm.mean[s * TS + tid] = sum;
+        }
+        if (prm.want_var) {
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.part[rg * TS + col_of(tm.cb, c)] = csq[c];
+            __syncthreads();
+            if (tid < TS && s * TS + tid < m) {
+                double sum = 0.0;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) sum += sm.part[g * TS + tid];
+                // prior variance of the latent function at x*: Noise contributes 0 (SAME = false)
+                int one_i[1] = {s * TS + tid}, one_j[1] = {s * TS + tid};
+                double kss[1][1];
+                eval_block<1, 1, false>(P, sm.sc, prm.Xs, m, m, one_i, prm.Xs, m, m, one_j, 0.0, kss);
+                prm.var[s * TS + tid] = kss[0][0] - sum;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// out (n x S) = L Z : grid = nt CTAs (tile row i), thread (row = tid % 64, sample lane = tid / 64)
+__global__ void __launch_bounds__(NTHREADS) sample_kernel(const double *tiles, int nt, int n, const double *Z, int S,
+                                                          double *out) {
+    __shared__ __align__(16) double T[TILE_ELEMS];
+    const int tid = threadIdx.x, i = blockIdx.x;
+    const int row = tid & (TS - 1), sl = tid >> 6;
+    for (int s0 = 0; s0 < S; s0 += 4) {
+        const int s = s0 + sl;
+        double acc = 0.0;
+        for (int k = 0; k <= i; ++k) {
+            __syncthreads();
+            tile_load_async(T, tiles + tri_index(i, k) * TILE_ELEMS, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            if (s < S) {
+                for (int kk = 0; kk < TS; ++kk) {
+                    const int g = k * TS + kk;
+                    const double z = g < n ? Z[(size_t)s * n + g] : 0.0;
+                    acc = fma(T[kk * TS + row], z, acc);
+                }
+            }
+        }
+        if (s < S && i * TS + row < n) out[(size_t)s * n + i * TS + row] = acc;
+    }
+}
+
+}  // namespace gpl

@@ -1,0 +1,157 @@
+/*
+ * gaplac_b200.h — C ABI of libgaplac_b200.so, the B200 (sm_100a) backend for GaPLAC's Gaussian-process
+ * marginal-likelihood / posterior hot path.
+ *
+ * The reference (biobakery/GaPLAC, pure Julia) has no FFI for this path; the boundary this library sits
+ * behind is the AbstractGPs/KernelFunctions call surface GaPLAC uses.  Each entry point
+ * below names the reference call it replaces (paths relative to the reference tree).  A Julia host binds
+ * them with `ccall` (julia/GaPLACB200.jl); in this repository the same symbols are bound
+ * with Python ctypes (gaplac_b200/_lib.py).
+ *
+ * Conventions
+ *   - all matrices column-major (Julia / LAPACK): X is n x d with leading dimension n, Theta is p x B,
+ *     Y is n x B, K is n x n;
+ *   - all host pointers are caller-owned; host entry points copy H2D/D2H on the context's stream and
+ *     return after the results are in the caller's buffers (blocking, like LAPACK);
+ *   - *_dev entry points take DEVICE pointers and a CUDA stream (cudaStream_t passed as void*) and return
+ *     after enqueueing (asynchronous); the caller synchronises the stream;
+ *   - every function returns GPL_OK (0) or a negative gpl_status; nothing throws or aborts;
+ *     gpl_last_error() gives the message.  Per-item numerical failures (matrix not positive definite) are
+ *     NOT API errors: they are reported LAPACK-style in info[b] (1-based failing pivot) with lml[b] = -Inf
+ *     (the Julia shim turns info != 0 into PosDefException(info), as `cholesky` does [upstream]).
+ *   - there is no CPU fallback: without a CUDA device gpl_init fails with GPL_ERR_CUDA.
+ */
+#ifndef GAPLAC_B200_H
+#define GAPLAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPL_ABI_VERSION 1
+
+typedef enum gpl_status {
+    GPL_OK = 0,
+    GPL_ERR_ARG = -1,     /* bad argument (null pointer, size, malformed program) */
+    GPL_ERR_CUDA = -2,    /* CUDA runtime error, or no usable device */
+    GPL_ERR_LIMIT = -3,   /* program too large (terms / factors / slots) or n beyond a kernel limit */
+    GPL_ERR_NOTPD = -4    /* single-model calls only: covariance not positive definite (info in message) */
+} gpl_status;
+
+/* Node kinds of the kernel-program: the leaves of src/gp_parts.jl:21-47 (SqExp, Linear, OU, Cat) with
+ * the k(x,x') of src/abstractgp_translations.jl:8-15 and src/gp_parts.jl:11-13, the two components the
+ * README/legacy fixtures name but the current src/ lacks (Constant, Noise), and the two
+ * operations of src/gp_parts.jl:55,59 (`+` -> :add, `*` -> :multiply). */
+typedef enum gpl_kind {
+    GPL_SQEXP = 0,    /* exp(-(x-x')^2 / (2 l^2))      hyperparameter l (> 0) */
+    GPL_OU = 1,       /* exp(-|x-x'| / l)               hyperparameter l (> 0) */
+    GPL_LINEAR = 2,   /* x x' + c                       hyperparameter c */
+    GPL_CAT = 3,      /* x == x' ? 1 : 0                none */
+    GPL_CONSTANT = 4, /* c                              hyperparameter c */
+    GPL_NOISE = 5,    /* delta_ij by row index on K(X,X); 0 on cross-covariances and on diag K(X*,X*) */
+    GPL_ADD = 6,      /* pops two, pushes lhs + rhs */
+    GPL_MUL = 7       /* pops two, pushes lhs * rhs */
+} gpl_kind;
+
+/* One postfix instruction.  The formula AST (src/gp_parts.jl:3-9) is flattened left to right, so the
+ * i-th leaf reads column `col` exactly as `kernel()` binds the i-th leaf to the i-th column with
+ * SelectTransform (src/abstractgp_translations.jl:45-71).  After a node's value is computed it is
+ * multiplied by a variance: theta[var_slot] if var_slot >= 0, else `var` (1.0 = reference semantics). */
+typedef struct gpl_op {
+    int32_t kind;       /* gpl_kind */
+    int32_t col;        /* input column of a leaf (ignored by CONSTANT, NOISE, ADD, MUL) */
+    int32_t theta_slot; /* slot of l / c in the per-item hyperparameter vector; -1: use `value` */
+    int32_t var_slot;   /* slot of the variance multiplier; -1: use `var` */
+    double value;       /* fixed hyperparameter when theta_slot < 0 */
+    double var;         /* fixed variance multiplier when var_slot < 0 */
+} gpl_op;
+
+#define GPL_MAX_OPS 64
+#define GPL_MAX_TERMS 16   /* additive terms after expansion to a sum of products */
+#define GPL_MAX_FACTORS 48 /* leaf / parameter factors over all terms */
+#define GPL_MAX_THETA 16   /* hyperparameter slots per item */
+#define GPL_MAX_COLS 16    /* input columns d */
+
+typedef struct gpl_ctx gpl_ctx;   /* device, stream, workspace pool */
+typedef struct gpl_prog gpl_prog; /* compiled kernel-program */
+typedef struct gpl_post gpl_post; /* posterior: Cholesky factor and alpha resident in HBM */
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* device = CUDA ordinal, or -1 for the current device.  Calls on one context serialise on its stream. */
+int gpl_init(int device, gpl_ctx **out);
+int gpl_destroy(gpl_ctx *ctx);
+const char *gpl_last_error(gpl_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
+int gpl_abi_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t gpl_launch_count(gpl_ctx *ctx);
+/* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant", "chol_variant" */
+int gpl_set_option(gpl_ctx *ctx, const char *key, int value);
+/* device facts for reports: name (<= len bytes), SM count, SM clock kHz */
+int gpl_device_info(gpl_ctx *ctx, char *name, int len, int *sm_count, int *clock_khz);
+
+/* ---- kernel program: replaces makekernel/_convert2eq/kernel (src/abstractgp_translations.jl:8-71) -- */
+int gpl_program_create(gpl_ctx *ctx, const gpl_op *ops, int n_ops, gpl_prog **out);
+int gpl_program_destroy(gpl_prog *prog);
+int gpl_program_n_theta(const gpl_prog *prog); /* 1 + highest slot referenced */
+int gpl_program_n_cols(const gpl_prog *prog);  /* 1 + highest column referenced */
+
+/* ---- covariance construction: replaces kernelmatrix(k, RowVecs(X)) + sigma2*I ----------------------
+ * [upstream KernelFunctions] reached from FiniteGP at CLI/src/mcmc.jl:35, CLI/src/select.jl:43,47,
+ * CLI/src/sample.jl:25, src/plotting.jl:6.  K (n x n) = K(X,X) + (sigma2 + jitter) I. */
+int gpl_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,
+            double sigma2, double jitter, double *K);
+int gpl_cov_dev(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *dX, const double *dtheta, int p,
+                double sigma2, double jitter, double *dK, void *stream);
+/* cross-covariance K(X, Xs) (n x m), Noise contributes 0: the K* of mean_and_var (src/plotting.jl:12) */
+int gpl_cross_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int m, int d, const double *X, const double *Xs,
+                  const double *theta, int p, double *Ks);
+
+/* ---- batched log marginal likelihood: replaces logpdf(FiniteGP, y) ------------------------------------
+ * [upstream AbstractGPs]; call sites CLI/src/select.jl:49-50 and, per leapfrog step, CLI/src/mcmc.jl:35.
+ *   lml[b] = -1/2 ( n log 2pi + logdet K_b + y_b' K_b^-1 y_b ),  K_b = K(X_b,X_b; theta_b) + (sigma2_b + jitter) I
+ * Batch modes: X shared (x_batched = 0, n x d) or per item (n x d x B); Y shared (n) or per item (n x B);
+ * sigma2 shared (1 value) or per item (B values); Theta always p x B.
+ * Optional analytic gradient (the reference gets it by ForwardDiff through the model body,
+ * CLI/src/mcmc.jl:31-37): dtheta (p x B) = dlml/dtheta, dy (n x B) = dlml/dy = -K^-1 y.  NULL to skip. */
+int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, int x_batched,
+                    const double *Y, int y_batched, const double *Theta, int p, const double *sigma2,
+                    int sigma2_batched, double jitter, int B, double *lml, double *dtheta, double *dy, int *info);
+int gpl_lml_batched_dev(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *dX, int x_batched,
+                        const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
+                        int sigma2_batched, double jitter, int B, double *dlml, double *ddtheta, double *ddy,
+                        int *dinfo, void *stream);
+
+/* ---- posterior: replaces posterior(FiniteGP, y) and mean_and_var(PosteriorGP, X*) ----------------------
+ * [upstream AbstractGPs]; call sites CLI/src/select.jl:51-52, src/plotting.jl:8 and src/plotting.jl:12.
+ * The factor and alpha = K^-1 y stay in HBM inside the handle. */
+int gpl_posterior_fit(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                      const double *theta, int p, double sigma2, double jitter, gpl_post **out);
+int gpl_posterior_free(gpl_post *post);
+int gpl_posterior_logpdf(gpl_post *post, double *lml);  /* logpdf from the same factorisation */
+int gpl_posterior_alpha(gpl_post *post, double *alpha); /* n values */
+int gpl_posterior_factor(gpl_post *post, double *U);    /* n x n upper factor (K = U'U), zeros below */
+/* mean[m] = K(X*,X) alpha ; var[m] = diag K(X*,X*) - colsumsq(U' \ K(X,X*)) (latent f; sigma2 not added).
+ * Xs is m x d column-major. var may be NULL. Tiled over m: K* is never materialised. */
+int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean, double *var);
+
+/* ---- prior sample: replaces rand(gp(X, sigma2)) (CLI/src/sample.jl:25) --------------------------------
+ * out (n x S) = U' Z with caller-supplied standard normals Z (n x S): the RNG stays in the host. */
+int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,
+               double sigma2, double jitter, const double *Z, int S, double *out);
+
+/* ---- single large-n factorisation (BASELINE config 5): cholesky(Symmetric(A)) + logdet -----------------
+ * A (n x n, column-major, symmetric; only the lower triangle is read) is overwritten by the upper factor U
+ * when `want_factor` != 0; logdet = 2 sum log U_ii.  *info = 0 or the failing pivot. */
+int gpl_chol_logdet(gpl_ctx *ctx, int n, double *A, int want_factor, double *logdet, int *info);
+int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo, void *stream);
+/* fused: build K_y from the program on the device, factor it, return logdet and lml without K ever
+ * crossing PCIe (the large-n model of config 5). */
+int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                  const double *theta, int p, double sigma2, double jitter, double *lml, double *logdet, int *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAPLAC_B200_H */
