@@ -31,6 +31,8 @@ struct __align__(16) LmlSmem {
     double rowbuf[2 * TS];
     double pivbuf[TS];
     double ybuf[TS];
+    double L16s[256];
+    double W16s[256];
     double gsum[GPL_MAX_THETA];
     double red[8];
     double logdet;
@@ -51,7 +53,10 @@ __device__ __forceinline__ double col_dot_diag(const double *T, const double *v,
 
 }  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
+// V = 0: first version (one barrier per pivot, single-buffered tile loads) — kept as the in-tree A/B reference.
+// V = 1: blocked warp-level diagonal factorisation, double-buffered half-tile loads, direct global stores.
+template <int V>
+__device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LmlSmem &sm = *reinterpret_cast<LmlSmem *>(smem_raw);
     const DevProgram &P = prm.prog;
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
         __syncthreads();
 
         // ------------------------------------------------------------------ factorisation ------------
+        if (V == 0)
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
                 double acc[4][4];
@@ -157,6 +163,92 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
                 }
             }
         }
+
+        if (V == 1)
+        for (int j = 0; j < nt; ++j) {
+            for (int i = j; i < nt; ++i) {
+                const bool diag = (i == j);
+                const int Q = 2 * j;  // half-steps: (k, h) = (q >> 1, q & 1), 32 columns of L_ik / L_jk each
+                const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1) are contiguous
+                const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;
+                // all readers of the staging buffers (previous tile) are done; start the first loads, then
+                // generate the covariance tile while they are in flight
+                __syncthreads();
+                if (Q > 0) {
+                    half_tile_load_async(sm.A, srcA, tid);
+                    if (!diag) half_tile_load_async(sm.Bt, srcB, tid);
+                    cp_async_commit();
+                }
+                double acc[4][4];
+                {
+                    int gi[4], gj[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) gi[r] = i * TS + tm.m0 + r;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) gj[c] = j * TS + col_of(tm.cb, c);
+                    eval_block<4, 4, true>(P, sm.sc, X, n, n, gi, X, n, n, gj, diag_add, acc);
+                }
+                double ytmp = 0.0;
+                if (diag && tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
+                for (int q = 0; q < Q; ++q) {
+                    cp_async_wait<0>();
+                    __syncthreads();  // half-step q landed for everyone; everyone finished half-step q-1
+                    if (q + 1 < Q) {
+                        const int nb = ((q + 1) & 1) * (TILE_ELEMS / 2);
+                        half_tile_load_async(sm.A + nb, srcA + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+                        if (!diag) half_tile_load_async(sm.Bt + nb, srcB + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+                        cp_async_commit();
+                    }
+                    const double *a = sm.A + (q & 1) * (TILE_ELEMS / 2);
+                    const double *bt = diag ? a : sm.Bt + (q & 1) * (TILE_ELEMS / 2);
+                    tile_gemm<true>(acc, a, bt, tm, 0, TS / 2);
+                    if (diag && tid < TS) {
+                        const double *zk = wsZ + q * (TS / 2);
+                        double s = 0.0;
+#pragma unroll 8
+                        for (int kk = 0; kk < TS / 2; ++kk) s = fma(a[kk * TS + tid], zk[kk], s);
+                        ytmp -= s;
+                    }
+                }
+                if (diag) {
+                    __syncthreads();  // staging buffers become the factorisation scratch
+                    double w[4][4];
+                    const int fail = tile_potrf_inv_blocked(acc, w, tm, sm.A, sm.L16s, sm.W16s, sm.colbuf, sm.pivbuf, tid);
+                    if (tid == 0 && fail >= 0 && sm.info == 0) sm.info = j * TS + fail + 1;
+                    acc_to_global(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
+                    acc_to_smem(sm.W, w, tm);
+                    if (tid < TS) sm.ybuf[tid] = ytmp;
+                    __syncthreads();
+                    if (tid < TS) {
+                        double s = 0.0;
+                        for (int c = 0; c <= tid; ++c) s = fma(sm.W[c * TS + tid], sm.ybuf[c], s);
+                        wsZ[j * TS + tid] = s;
+                    }
+                    if (tid < 32) {
+                        double lg = log(sm.pivbuf[tid]) + log(sm.pivbuf[tid + 32]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+                        if (tid == 0) sm.logdet += lg;
+                    }
+                    if (prm.want_grad || prm.keep) tile_store(wsW + (size_t)j * TILE_ELEMS, sm.W, tid);
+                } else {
+                    // L_ij = T_ij * W_jj' through shared memory (T staged in the load buffer), result stored
+                    // straight from registers
+                    __syncthreads();
+                    acc_to_smem(sm.A, acc, tm);
+                    __syncthreads();
+                    double x[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) x[r][c] = 0.0;
+                    const int kmax = ((tid >> 5) & 1) * 32 + 32;
+                    tile_gemm<false>(x, sm.A, sm.W, tm, 0, kmax);
+                    acc_to_global(wsL + tri_index(i, j) * TILE_ELEMS, x, tm);
+                }
+            }
+        }
+        __syncthreads();
 
         // ------------------------------------------------------------------ lml ----------------------
         double q = 0.0;
@@ -296,6 +388,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
         __syncthreads();
         if (tid < prm.p) prm.dtheta[(size_t)b * prm.p + tid] = info ? NAN : -0.5 * sm.gsum[tid];
     }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
+    lml_batched_body<1>(prm);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel_v0(const __grid_constant__ LmlParams prm) {
+    lml_batched_body<0>(prm);
 }
 
 size_t lml_smem_bytes() { return sizeof(LmlSmem); }

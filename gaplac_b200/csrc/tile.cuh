@@ -194,6 +194,222 @@ __device__ __forceinline__ int tile_potrf_inv(double (&acc)[4][4], double (&w)[4
     return fail;
 }
 
+// ---- Cholesky of the diagonal tile, blocked (v1) -------------------------------------------------------------
+// Same contract as tile_potrf_inv, but the 64 x 64 tile is processed in four 16-column panels:
+//   1. the owners of the panel's columns (acc) and of the panel's rows of the running inverse (w) publish them;
+//   2. warp 0 factors the 16 x 16 diagonal block in registers (one row per lane, pivots and columns exchanged
+//      with warp shuffles: no block barrier inside) and inverts it;
+//   3. all threads form the panel of L below the block (P * W16') and the new rows of the inverse (W16 * R);
+//   4. all threads apply the rank-16 update to their register blocks of the trailing tile and of the inverse.
+// Three block barriers per panel (12 per tile instead of 64) and the O(64^3) part runs as register-tiled FMAs.
+// scratch: 8192 doubles (two ping-pong sets of P, R, Lp, Rp); L16s / W16s: 256 doubles each; rsbuf: 16; pivbuf: 64.
+template <int H>
+__device__ __forceinline__ void gemm16_half(double (&c)[4][4], const double *__restrict__ A,
+                                            const double *__restrict__ B, TMap tm) {
+    const double *pa = A + tm.m0;
+    const double *pb = B + tm.cb + 16 * H;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(pa + k * TS);
+        const double2 a23 = *reinterpret_cast<const double2 *>(pa + k * TS + 2);
+        const double2 b = *reinterpret_cast<const double2 *>(pb + k * TS);
+        c[0][2 * H] = fma(-a01.x, b.x, c[0][2 * H]);
+        c[0][2 * H + 1] = fma(-a01.x, b.y, c[0][2 * H + 1]);
+        c[1][2 * H] = fma(-a01.y, b.x, c[1][2 * H]);
+        c[1][2 * H + 1] = fma(-a01.y, b.y, c[1][2 * H + 1]);
+        c[2][2 * H] = fma(-a23.x, b.x, c[2][2 * H]);
+        c[2][2 * H + 1] = fma(-a23.x, b.y, c[2][2 * H + 1]);
+        c[3][2 * H] = fma(-a23.y, b.x, c[3][2 * H]);
+        c[3][2 * H + 1] = fma(-a23.y, b.y, c[3][2 * H + 1]);
+    }
+}
+
+template <int P_, int H>
+__device__ __forceinline__ void potrf_panel_update(double (&acc)[4][4], double (&w)[4][4], TMap tm, int wr, int wc,
+                                                   const double *Lp, const double *Rp) {
+    const int pc = 2 * wc + H;  // 16-column panel this half of the thread's columns belongs to
+    if (pc == P_) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double *src = Lp + (col_of(tm.cb, 2 * H + q) - 16 * P_) * TS + tm.m0;
+            const double2 v01 = *reinterpret_cast<const double2 *>(src);
+            const double2 v23 = *reinterpret_cast<const double2 *>(src + 2);
+            acc[0][2 * H + q] = v01.x;
+            acc[1][2 * H + q] = v01.y;
+            acc[2][2 * H + q] = v23.x;
+            acc[3][2 * H + q] = v23.y;
+        }
+    } else if (pc > P_ && wr >= pc) {
+        gemm16_half<H>(acc, Lp, Lp, tm);
+    }
+    if (pc <= P_) {
+        if (wr > P_) {
+            gemm16_half<H>(w, Lp, Rp, tm);
+        } else if (wr == P_) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double2 v = *reinterpret_cast<const double2 *>(Rp + (tm.m0 + r - 16 * P_) * TS + tm.cb + 16 * H);
+                w[r][2 * H] = v.x;
+                w[r][2 * H + 1] = v.y;
+            }
+        }
+    }
+}
+
+template <int P_>
+__device__ __forceinline__ void potrf_panel(double (&acc)[4][4], double (&w)[4][4], TMap tm, double *scratch,
+                                            double *L16s, double *W16s, double *rsbuf, double *pivbuf, int tid, int &fail) {
+    const int warp = tid >> 5, lane = tid & 31, wr = warp >> 1, wc = warp & 1;
+    double *P = scratch + (P_ & 1) * 4096;  // 64 x 16 column-major: P[k*64 + row]
+    double *R = P + 1024;                   // 16 x 64: R[k*64 + col]
+    double *Lp = P + 2048;                  // 64 x 16 column-major
+    double *Rp = P + 3072;                  // 16 x 64
+    // 1. publish the panel's columns of the tile and the panel's rows of the running inverse
+    if (wc == (P_ >> 1)) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int cc = (P_ & 1) * 2 + q;
+            double *dst = P + (col_of(tm.cb, cc) - 16 * P_) * TS + tm.m0;
+            *reinterpret_cast<double2 *>(dst) = make_double2(acc[0][cc], acc[1][cc]);
+            *reinterpret_cast<double2 *>(dst + 2) = make_double2(acc[2][cc], acc[3][cc]);
+        }
+    }
+    if (wr == P_) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double *dst = R + (tm.m0 + r - 16 * P_) * TS + tm.cb;
+            *reinterpret_cast<double2 *>(dst) = make_double2(w[r][0], w[r][1]);
+            *reinterpret_cast<double2 *>(dst + 16) = make_double2(w[r][2], w[r][3]);
+        }
+    }
+    __syncthreads();
+    // 2. warp 0: Cholesky of the 16 x 16 diagonal block (row per lane, shuffles) and its inverse
+    if (warp == 0) {
+        const int r = lane & 15;
+        double a[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] = P[c * TS + 16 * P_ + r];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            double piv = __shfl_sync(0xffffffffu, a[c], c);
+            if (!(piv > 0.0)) {
+                if (fail < 0) fail = 16 * P_ + c;
+                piv = 1.0;
+            }
+            if (lane == 0) pivbuf[16 * P_ + c] = piv;
+            const double rs = rsqrt(piv);
+            if (lane == 0) rsbuf[c] = rs;
+            const double l = a[c] * rs;
+            a[c] = (r >= c) ? l : 0.0;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 16; ++c2) {
+                const double l2 = __shfl_sync(0xffffffffu, l, c2);
+                a[c2] = fma(-l, l2, a[c2]);
+            }
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) L16s[c * 16 + r] = a[c];
+        }
+        __syncwarp();
+        // column r of the inverse by forward substitution (axpy form): x = L16^-1 e_r
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            x[c] *= rsbuf[c];
+#pragma unroll
+            for (int i = c + 1; i < 16; ++i) x[i] = fma(-L16s[c * 16 + i], x[c], x[i]);
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) W16s[i * 16 + r] = x[i];  // W16[i][r], row-major
+        }
+    }
+    __syncthreads();
+    // 3a. panel of L: rows below the block = P * W16', rows of the block = L16, rows above = 0
+    {
+        const int row = tid & 63, cg = tid >> 6;
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (row >= 16 * (P_ + 1)) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double pk = P[k * TS + row];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = 4 * cg + q;
+                    if (k <= c) out[q] = fma(pk, W16s[c * 16 + k], out[q]);
+                }
+            }
+        } else if (row >= 16 * P_) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = L16s[(4 * cg + q) * 16 + (row - 16 * P_)];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Lp[(4 * cg + q) * TS + row] = out[q];
+    }
+    // 3b. new rows of the inverse: Rp = W16 * R
+    {
+        const int col = tid & 63, kg = tid >> 6;
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const double rv = R[k2 * TS + col];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 4 * kg + q;
+                if (k2 <= k) out[q] = fma(W16s[k * 16 + k2], rv, out[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Rp[(4 * kg + q) * TS + col] = out[q];
+    }
+    __syncthreads();
+    // 4. rank-16 updates of the register blocks
+    potrf_panel_update<P_, 0>(acc, w, tm, wr, wc, Lp, Rp);
+    potrf_panel_update<P_, 1>(acc, w, tm, wr, wc, Lp, Rp);
+}
+
+__device__ __forceinline__ int tile_potrf_inv_blocked(double (&acc)[4][4], double (&w)[4][4], TMap tm,
+                                                      double *scratch, double *L16s, double *W16s, double *rsbuf,
+                                                      double *pivbuf, int tid) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[r][c] = (tm.m0 + r == col_of(tm.cb, c)) ? 1.0 : 0.0;
+    int fail = -1;
+    potrf_panel<0>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
+    potrf_panel<1>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
+    potrf_panel<2>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
+    potrf_panel<3>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (col_of(tm.cb, c) > tm.m0 + r) acc[r][c] = 0.0;
+    return fail;  // meaningful in warp 0 (tid 0 reports it)
+}
+
+// register block -> global tile, column-major (each thread: 4 x 32 contiguous bytes)
+__device__ __forceinline__ void acc_to_global(double *__restrict__ tile, const double (&acc)[4][4], TMap tm) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        double *p = tile + col_of(tm.cb, cc) * TS + tm.m0;
+        *reinterpret_cast<double2 *>(p) = make_double2(acc[0][cc], acc[1][cc]);
+        *reinterpret_cast<double2 *>(p + 2) = make_double2(acc[2][cc], acc[3][cc]);
+    }
+}
+
+// asynchronous copy of one half (32 columns = 16 KiB) of a tile
+__device__ __forceinline__ void half_tile_load_async(double *smem, const double *__restrict__ gmem, int tid) {
+#pragma unroll
+    for (int it = 0; it < TILE_BYTES / 2 / 16 / NTHREADS; ++it) {
+        const int idx = it * NTHREADS + tid;
+        cp_async16(reinterpret_cast<char *>(smem) + idx * 16, reinterpret_cast<const char *>(gmem) + idx * 16);
+    }
+}
+
 // deterministic block-wide sum (256 threads), result valid in every thread; red = 8 doubles of shared memory
 __device__ __forceinline__ double block_sum(double v, double *red, int tid) {
 #pragma unroll
