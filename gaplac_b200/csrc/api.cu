@@ -118,12 +118,10 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     bool &attr_set = ctx->attr_lml;
     if (!attr_set) {
         CU(ctx, cudaFuncSetAttribute(lml_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(ctx, cudaFuncSetAttribute(lml_batched_kernel_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const bool v0 = ctx->lml_variant == 100;
     int occ = 0;
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v0 ? lml_batched_kernel_v0 : lml_batched_kernel, NTHREADS, smem));
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_kernel, NTHREADS, smem));
     if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "lml kernel does not fit on an SM (smem %zu)", smem);
     int grid = ctx->sm_count * occ;
     if (grid > B) grid = B;
@@ -165,8 +163,7 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     prm.dtheta = ddtheta;
     prm.dy = ddy;
     prm.info = dinfo;
-    if (v0) lml_batched_kernel_v0<<<grid, NTHREADS, smem, st>>>(prm);
-    else lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return GPL_OK;

@@ -18,24 +18,13 @@ struct __align__(16) BigSmem {
     double A[TILE_ELEMS];
     double Bt[TILE_ELEMS];
     double W[TILE_ELEMS];
-    double colbuf[2 * TS];
-    double rowbuf[2 * TS];
+    double rsbuf[16];
     double pivbuf[TS];
     double ybuf[TS];
+    double L16s[256];
+    double W16s[256];
 };
 
-__device__ __forceinline__ void acc_from_smem(double (&acc)[4][4], const double *T, TMap tm) {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const double *p = T + col_of(tm.cb, cc) * TS + tm.m0;
-        const double2 v01 = *reinterpret_cast<const double2 *>(p);
-        const double2 v23 = *reinterpret_cast<const double2 *>(p + 2);
-        acc[0][cc] = v01.x;
-        acc[1][cc] = v01.y;
-        acc[2][cc] = v23.x;
-        acc[3][cc] = v23.y;
-    }
-}
 }  // namespace
 
 size_t big_smem_bytes() { return sizeof(BigSmem); }
@@ -43,10 +32,8 @@ size_t big_smem_bytes() { return sizeof(BigSmem); }
 __global__ void __launch_bounds__(NTHREADS) dense_to_tiles_kernel(const double *__restrict__ A, int n, int nt,
                                                                   double *__restrict__ tiles) {
     const long long t = blockIdx.x;
-    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (tri_index(i + 1, 0) <= t) ++i;
-    while (tri_index(i, 0) > t) --i;
-    const int j = (int)(t - tri_index(i, 0));
+    int i, j;
+    tri_unrank(t, i, j);
     double *tile = tiles + t * TILE_ELEMS;
     for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
         const int r = e & (TS - 1), c = e >> 6;
@@ -62,7 +49,7 @@ __global__ void __launch_bounds__(NTHREADS) dense_to_tiles_kernel(const double *
             }
             v = A[(size_t)gc * n + gr];
         }
-        tile[e] = v;
+        tile[tidx(r, c)] = v;
     }
 }
 
@@ -72,7 +59,7 @@ __global__ void __launch_bounds__(NTHREADS) tiles_to_upper_kernel(const double *
     const int ti = blockIdx.x, tj = blockIdx.y;  // block (ti, tj) of U: rows ti*64.., cols tj*64..
     if (ti <= tj) {
         const double *tile = tiles + tri_index(tj, ti) * TILE_ELEMS;  // L block (tj, ti)
-        for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) T[e >> 6][e & (TS - 1)] = tile[e];  // T[c][r]
+        for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) T[e >> 6][e & (TS - 1)] = tile[tidx(e & (TS - 1), e >> 6)];  // T[c][r]
     }
     __syncthreads();
     for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
@@ -95,35 +82,28 @@ __global__ void __launch_bounds__(NTHREADS) big_diag_kernel(BigParams prm) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[4][4];
-    acc_from_smem(acc, sm.A, tm);
+    double acc[2][8];
+    acc_from_tile(acc, sm.A, tm);
     for (int k = prm.k0; k < j; ++k) {
         __syncthreads();
         tile_load_async(sm.A, prm.tiles + tri_index(j, k) * TILE_ELEMS, tid);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
-        tile_gemm<true>(acc, sm.A, sm.A, tm, 0, TS);
+        tile_mma<true>(acc, sm.A, sm.A, tm, 0, TS);
     }
     __syncthreads();
-    double w[4][4];
-    const int fail = tile_potrf_inv(acc, w, tm, sm.colbuf, sm.rowbuf, sm.pivbuf, tid);
+    double w[2][8];
+    const int fail = tile_potrf_inv(acc, w, tm, sm.A, sm.L16s, sm.W16s, sm.rsbuf, sm.pivbuf, tid);
     if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
-    acc_to_smem(sm.A, acc, tm);
-    acc_to_smem(sm.W, w, tm);
+    acc_to_tile(Tjj, acc, tm);
+    acc_to_tile(sm.W, w, tm);
+    if (prm.y && tid < TS) sm.ybuf[tid] = prm.y[j * TS + tid];
     __syncthreads();
-    tile_store(Tjj, sm.A, tid);
     tile_store(prm.winv + (size_t)j * TILE_ELEMS, sm.W, tid);
     if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
-    if (prm.y && tid < TS) {
-        // z_j = W_jj y_j (y_j already carries the updates of all earlier tile columns)
-        const double *yj = prm.y + j * TS;
-        double s = 0.0;
-        for (int c = 0; c <= tid; ++c) s = fma(sm.W[c * TS + tid], yj[c], s);
-        sm.ybuf[tid] = s;
-    }
-    __syncthreads();
-    if (prm.y && tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+    // z_j = W_jj y_j (y_j already carries the updates of all earlier tile columns)
+    if (prm.y && tid < TS) prm.y[j * TS + tid] = tile_row_dot(sm.W, sm.ybuf, tid, 0, tid + 1);
 }
 
 // tiles (i, j), i > j: left-looking update inside the panel, then L_ij = T_ij W_jj', then y_i -= L_ij z_j
@@ -138,8 +118,8 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[4][4];
-    acc_from_smem(acc, sm.A, tm);
+    double acc[2][8];
+    acc_from_tile(acc, sm.A, tm);
     for (int k = prm.k0; k < j; ++k) {
         __syncthreads();
         tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
@@ -147,65 +127,56 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
-        tile_gemm<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+        tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
     __syncthreads();
-    acc_to_smem(sm.A, acc, tm);
+    acc_to_tile(sm.A, acc, tm);
     __syncthreads();
-    double x[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) x[r][c] = 0.0;
-    const int kmax = ((tid >> 5) & 1) * 32 + 32;
-    tile_gemm<false>(x, sm.A, sm.W, tm, 0, kmax);
-    __syncthreads();
-    acc_to_smem(sm.A, x, tm);
-    __syncthreads();
-    tile_store(Tij, sm.A, tid);
-    if (prm.y && tid < TS) {
-        const double *zj = prm.y + j * TS;
-        double s = 0.0;
-#pragma unroll 8
-        for (int kk = 0; kk < TS; ++kk) s = fma(sm.A[kk * TS + tid], zj[kk], s);
-        prm.y[i * TS + tid] -= s;
+    double x[2][8];
+    acc_zero(x);
+    tile_mma<false>(x, sm.A, sm.W, tm, 0, tm.c0 + 32);
+    acc_to_tile(Tij, x, tm);
+    if (prm.y) {
+        __syncthreads();
+        acc_to_tile(sm.A, x, tm);
+        __syncthreads();
+        if (tid < TS) prm.y[i * TS + tid] -= tile_row_dot(sm.A, prm.y + j * TS, tid, 0, TS);
     }
 }
 
 // trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'
-__global__ void __launch_bounds__(NTHREADS) big_trail_kernel(BigParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 2) big_trail_kernel(BigParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
-    const long long t = blockIdx.x;
-    int ii = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (tri_index(ii + 1, 0) <= t) ++ii;
-    while (tri_index(ii, 0) > t) --ii;
-    const int ll = (int)(t - tri_index(ii, 0));
+    int ii, ll;
+    tri_unrank(blockIdx.x, ii, ll);
     const int i = prm.j1 + ii, l = prm.j1 + ll;
+    const bool diag = (i == l);
     double *Til = prm.tiles + tri_index(i, l) * TILE_ELEMS;
-    tile_load_async(sm.W, Til, tid);
+    const int Q = 2 * (prm.j1 - prm.k0);  // half-steps of 32 panel columns; the panel's tiles of a row are contiguous
+    const double *srcA = prm.tiles + tri_index(i, prm.k0) * TILE_ELEMS;
+    const double *srcB = prm.tiles + tri_index(l, prm.k0) * TILE_ELEMS;
+    half_tile_load_async(sm.A, srcA, tid);
+    if (!diag) half_tile_load_async(sm.Bt, srcB, tid);
     cp_async_commit();
-    double acc[4][4];
-    bool first = true;
-    for (int k = prm.k0; k < prm.j1; ++k) {
-        __syncthreads();
-        tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
-        if (i != l) tile_load_async(sm.Bt, prm.tiles + tri_index(l, k) * TILE_ELEMS, tid);
-        cp_async_commit();
+    double acc[2][8];
+    acc_from_tile(acc, Til, tm);  // straight from global / L2 into the accumulator registers
+    for (int q = 0; q < Q; ++q) {
         cp_async_wait<0>();
         __syncthreads();
-        if (first) {
-            acc_from_smem(acc, sm.W, tm);
-            first = false;
+        if (q + 1 < Q) {
+            const int nb = ((q + 1) & 1) * (TILE_ELEMS / 2);
+            half_tile_load_async(sm.A + nb, srcA + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+            if (!diag) half_tile_load_async(sm.Bt + nb, srcB + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+            cp_async_commit();
         }
-        tile_gemm<true>(acc, sm.A, (i == l) ? sm.A : sm.Bt, tm, 0, TS);
+        const double *a = sm.A + (q & 1) * (TILE_ELEMS / 2);
+        const double *bt = diag ? a : sm.Bt + (q & 1) * (TILE_ELEMS / 2);
+        tile_mma<true>(acc, a, bt, tm, 0, TS / 2);
     }
-    __syncthreads();
-    acc_to_smem(sm.A, acc, tm);
-    __syncthreads();
-    tile_store(Til, sm.A, tid);
+    acc_to_tile(Til, acc, tm);
 }
 
 // backward substitution, one launch per tile row i (descending), grid = i + 1: every CTA recomputes
@@ -222,14 +193,7 @@ __global__ void __launch_bounds__(NTHREADS) big_backward_kernel(const double *ti
     cp_async_wait<0>();
     if (tid < TS) v[tid] = r[i * TS + tid];
     __syncthreads();
-    if (tid < TS) {
-        double s = 0.0;
-        for (int t = 0; t < TS; ++t) {
-            const int m = (tid + t) & (TS - 1);
-            s = fma(T[tid * TS + m], v[m], s);
-        }
-        a[tid] = s;
-    }
+    if (tid < TS) a[tid] = tile_col_dot(T, v, tid);
     __syncthreads();
     if (j == i) {
         if (tid < TS) alpha[i * TS + tid] = a[tid];
@@ -239,14 +203,7 @@ __global__ void __launch_bounds__(NTHREADS) big_backward_kernel(const double *ti
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    if (tid < TS) {
-        double s = 0.0;
-        for (int t = 0; t < TS; ++t) {
-            const int m = (tid + t) & (TS - 1);
-            s = fma(T[tid * TS + m], a[m], s);
-        }
-        r[j * TS + tid] -= s;
-    }
+    if (tid < TS) r[j * TS + tid] -= tile_col_dot(T, a, tid);
 }
 
 __global__ void __launch_bounds__(NTHREADS) big_reduce_kernel(const double *pivlog, const double *z, int len,

@@ -10,37 +10,31 @@
 
 namespace gpl {
 
-// dense column-major output; grid = (ceil(na/64), ceil(nb/64)); each thread stores 4 consecutive rows
-// (32 B) of 4 columns, a warp covers 128 B contiguous per column.
+// dense column-major output; grid = (ceil(na/64), ceil(nb/64)).  A warp stores, per (row block, column), 8
+// consecutive rows (64 B) of 4 columns.
 __global__ void __launch_bounds__(NTHREADS) cov_dense_kernel(const __grid_constant__ CovParams prm) {
     __shared__ ItemScalars sc;
     const int tid = threadIdx.x;
     prepare_item_scalars(prm.prog, prm.theta, &sc, tid);
     __syncthreads();
     const TMap tm = thread_map(tid);
-    int gi[4], gj[4];
+    int gi[2], gj[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) gi[r] = blockIdx.x * TS + tm.m0 + r;
+    for (int mb = 0; mb < 2; ++mb) gi[mb] = blockIdx.x * TS + row_of(tm, mb);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) gj[c] = blockIdx.y * TS + col_of(tm.cb, c);
-    double acc[4][4];
+    for (int cc = 0; cc < 8; ++cc) gj[cc] = blockIdx.y * TS + col_of(tm, cc);
+    double acc[2][8];
     if (prm.same)
-        eval_block<4, 4, true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, prm.diag_add, acc);
+        eval_block<2, 8, true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, prm.diag_add, acc);
     else
-        eval_block<4, 4, false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, 0.0, acc);
-    const bool vec_ok = (prm.na % 2 == 0) && (gi[3] < prm.na);
+        eval_block<2, 8, false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, 0.0, acc);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (gj[c] >= prm.nb) continue;
-        double *col = prm.K + (size_t)gj[c] * prm.na;
-        if (vec_ok) {
-            *reinterpret_cast<double2 *>(col + gi[0]) = make_double2(acc[0][c], acc[1][c]);
-            *reinterpret_cast<double2 *>(col + gi[2]) = make_double2(acc[2][c], acc[3][c]);
-        } else {
+    for (int cc = 0; cc < 8; ++cc) {
+        if (gj[cc] >= prm.nb) continue;
+        double *col = prm.K + (size_t)gj[cc] * prm.na;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (gi[r] < prm.na) col[gi[r]] = acc[r][c];
-        }
+        for (int mb = 0; mb < 2; ++mb)
+            if (gi[mb] < prm.na) col[gi[mb]] = acc[mb][cc];
     }
 }
 
@@ -50,27 +44,18 @@ __global__ void __launch_bounds__(NTHREADS) cov_tiles_kernel(const __grid_consta
     const int tid = threadIdx.x;
     prepare_item_scalars(prm.prog, prm.theta, &sc, tid);
     __syncthreads();
-    // linear tile index -> (i, j), i >= j
     const long long t = blockIdx.x;
-    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (tri_index(i + 1, 0) <= t) ++i;
-    while (tri_index(i, 0) > t) --i;
-    const int j = (int)(t - tri_index(i, 0));
+    int i, j;
+    tri_unrank(t, i, j);
     const TMap tm = thread_map(tid);
-    int gi[4], gj[4];
+    int gi[2], gj[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) gi[r] = i * TS + tm.m0 + r;
+    for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) gj[c] = j * TS + col_of(tm.cb, c);
-    double acc[4][4];
-    eval_block<4, 4, true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, gj, prm.diag_add, acc);
-    double *tile = prm.tiles + t * TILE_ELEMS;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double *p = tile + col_of(tm.cb, c) * TS + tm.m0;
-        *reinterpret_cast<double2 *>(p) = make_double2(acc[0][c], acc[1][c]);
-        *reinterpret_cast<double2 *>(p + 2) = make_double2(acc[2][c], acc[3][c]);
-    }
+    for (int cc = 0; cc < 8; ++cc) gj[cc] = j * TS + col_of(tm, cc);
+    double acc[2][8];
+    eval_block<2, 8, true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, gj, prm.diag_add, acc);
+    acc_to_tile(prm.tiles + t * TILE_ELEMS, acc, tm);
 }
 
 }  // namespace gpl

@@ -23,8 +23,7 @@ struct LmlParams {
     int *info;
     unsigned int *counter;  // dynamic work distribution (NULL: item = blockIdx.x)
 };
-__global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);     // current
-__global__ void lml_batched_kernel_v0(const __grid_constant__ LmlParams prm);  // first version, kept for A/B (lml_variant = 100)
+__global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);
 size_t lml_smem_bytes();
 
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------

@@ -17,7 +17,7 @@ namespace {
 struct __align__(16) PredSmem {
     double A[TILE_ELEMS];
     double Bt[TILE_ELEMS];
-    double part[16 * TS];  // per row-group partial column sums
+    double part[32 * TS];  // per (row band, lane group) partial column sums
     ItemScalars sc;
 };
 }  // namespace
@@ -31,31 +31,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
     const int n = prm.n, nt = prm.nt, m = prm.m;
-    const int rg = tm.m0 >> 2;  // row group 0..15
     double *wsV = prm.wsV + (size_t)blockIdx.x * nt * TILE_ELEMS;
     prepare_item_scalars(P, prm.theta, &sm.sc, tid);
     __syncthreads();
 
     const int nslab = (m + TS - 1) / TS;
     for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
-        int gj[4];
+        int gj[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gj[c] = s * TS + col_of(tm.cb, c);
-        double csq[4] = {0.0, 0.0, 0.0, 0.0}, cmean[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int cc = 0; cc < 8; ++cc) gj[cc] = s * TS + col_of(tm, cc);
+        double csq[8], cmean[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) csq[cc] = cmean[cc] = 0.0;
         for (int i = 0; i < nt; ++i) {
-            int gi[4];
+            int gi[2];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) gi[r] = i * TS + tm.m0 + r;
-            double acc[4][4];
-            eval_block<4, 4, false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
+            for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
+            double acc[2][8];
+            eval_block<2, 8, false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const double al = gi[r] < n ? prm.alpha[gi[r]] : 0.0;
+            for (int mb = 0; mb < 2; ++mb) {
+                const double al = gi[mb] < n ? prm.alpha[gi[mb]] : 0.0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) cmean[c] = fma(acc[r][c], al, cmean[c]);
+                for (int cc = 0; cc < 8; ++cc) cmean[cc] = fma(acc[mb][cc], al, cmean[cc]);
             }
             if (!prm.want_var) continue;
-            // acc -= sum_{k<i} L_ik V_k   (V_k stored transposed: element (kk, col) at kk*64 + col)
+            // acc -= sum_{k<i} L_ik V_k : row operand L_ik, column operand V_k' (stored transposed)
             for (int k = 0; k < i; ++k) {
                 __syncthreads();
                 tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
@@ -63,53 +64,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncthreads();
-                tile_gemm<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+                tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
             }
-            // V_i = W_ii acc  (W lower triangular: row m needs kk <= m)
+            // V_i = W_ii acc  (W lower triangular: rows of this warp need k < r0 + 16)
             __syncthreads();
             tile_load_async(sm.A, prm.winv + (size_t)i * TILE_ELEMS, tid);
             cp_async_commit();
-            acc_to_smem_t(sm.Bt, acc, tm);
+            acc_to_tile_t(sm.Bt, acc, tm);
             cp_async_wait<0>();
             __syncthreads();
-            double v[4][4];
+            double v[2][8];
+            acc_zero(v);
+            tile_mma<false>(v, sm.A, sm.Bt, tm, 0, tm.r0 + 16);
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[r][c] = 0.0;
-            const int kmax = ((tid >> 6) + 1) * 16;  // rows of this warp are < kmax
-            tile_gemm<false>(v, sm.A, sm.Bt, tm, 0, kmax);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) csq[c] = fma(v[r][c], v[r][c], csq[c]);
-            if (i + 1 < nt) {
-                __syncthreads();
-                acc_to_smem_t(sm.A, v, tm);
-                __syncthreads();
-                tile_store(wsV + (size_t)i * TILE_ELEMS, sm.A, tid);
-            }
+                for (int cc = 0; cc < 8; ++cc) csq[cc] = fma(v[mb][cc], v[mb][cc], csq[cc]);
+            if (i + 1 < nt) acc_to_tile_t(wsV + (size_t)i * TILE_ELEMS, v, tm);
         }
-        // reduce the per-thread partials over the 16 row groups (deterministic order)
+        // reduce the per-thread partials: 32 partials per column (4 row bands x 8 lanes g), fixed order
+        const int slot = (tid >> 6) * 8 + tm.g;
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sm.part[rg * TS + col_of(tm.cb, c)] = cmean[c];
+        for (int cc = 0; cc < 8; ++cc) sm.part[slot * TS + col_of(tm, cc)] = cmean[cc];
         __syncthreads();
         if (tid < TS && s * TS + tid < m) {
             double sum = 0.0;
-#pragma unroll
-            for (int g = 0; g < 16; ++g) sum += sm.part[g * TS + tid];
+#pragma unroll 8
+            for (int gq = 0; gq < 32; ++gq) sum += sm.part[gq * TS + tid];
             prm.mean[s * TS + tid] = sum;
         }
         if (prm.want_var) {
             __syncthreads();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sm.part[rg * TS + col_of(tm.cb, c)] = csq[c];
+            for (int cc = 0; cc < 8; ++cc) sm.part[slot * TS + col_of(tm, cc)] = csq[cc];
             __syncthreads();
             if (tid < TS && s * TS + tid < m) {
                 double sum = 0.0;
-#pragma unroll
-                for (int g = 0; g < 16; ++g) sum += sm.part[g * TS + tid];
+#pragma unroll 8
+                for (int gq = 0; gq < 32; ++gq) sum += sm.part[gq * TS + tid];
                 // prior variance of the latent function at x*: Noise contributes 0 (SAME = false)
                 int one_i[1] = {s * TS + tid}, one_j[1] = {s * TS + tid};
                 double kss[1][1];
@@ -140,7 +133,7 @@ __global__ void __launch_bounds__(NTHREADS) sample_kernel(const double *tiles, i
                 for (int kk = 0; kk < TS; ++kk) {
                     const int g = k * TS + kk;
                     const double z = g < n ? Z[(size_t)s * n + g] : 0.0;
-                    acc = fma(T[kk * TS + row], z, acc);
+                    acc = fma(T[tidx(row, kk)], z, acc);
                 }
             }
         }
