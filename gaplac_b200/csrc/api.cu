@@ -114,14 +114,18 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     const long long tiles_per_cta = ntri + nt + (want_grad ? ntri : 0);
-    const size_t smem = lml_smem_bytes();
+    const size_t smem = lml_smem_bytes(want_grad != 0);
     bool &attr_set = ctx->attr_lml;
     if (!attr_set) {
-        CU(ctx, cudaFuncSetAttribute(lml_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(lml_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)lml_smem_bytes(false)));
+        CU(ctx, cudaFuncSetAttribute(lml_batched_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)lml_smem_bytes(true)));
         attr_set = true;
     }
     int occ = 0;
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_kernel, NTHREADS, smem));
+    if (want_grad) CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_grad_kernel, NTHREADS, smem));
+    else CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_kernel, NTHREADS, smem));
     if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "lml kernel does not fit on an SM (smem %zu)", smem);
     int grid = ctx->sm_count * occ;
     if (grid > B) grid = B;
@@ -163,7 +167,8 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     prm.dtheta = ddtheta;
     prm.dy = ddy;
     prm.info = dinfo;
-    lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    if (want_grad) lml_batched_grad_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    else lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return GPL_OK;

@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(NTHREADS) cov_dense_kernel(const __grid_consta
     for (int cc = 0; cc < 8; ++cc) gj[cc] = blockIdx.y * TS + col_of(tm, cc);
     double acc[2][8];
     if (prm.same)
-        eval_block<2, 8, true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, prm.diag_add, acc);
+        eval_block_2x8<true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, prm.diag_add, acc);
     else
-        eval_block<2, 8, false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, 0.0, acc);
+        eval_block_2x8<false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, 0.0, acc);
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
         if (gj[cc] >= prm.nb) continue;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NTHREADS) cov_tiles_kernel(const __grid_consta
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) gj[cc] = j * TS + col_of(tm, cc);
     double acc[2][8];
-    eval_block<2, 8, true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, gj, prm.diag_add, acc);
+    eval_block_2x8<true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, gj, prm.diag_add, acc);
     acc_to_tile(prm.tiles + t * TILE_ELEMS, acc, tm);
 }
 

@@ -23,8 +23,9 @@ struct LmlParams {
     int *info;
     unsigned int *counter;  // dynamic work distribution (NULL: item = blockIdx.x)
 };
-__global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);
-size_t lml_smem_bytes();
+__global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);       // lml (+ keep): 3 CTAs / SM
+__global__ void lml_batched_grad_kernel(const __grid_constant__ LmlParams prm);  // lml + gradient: 2 CTAs / SM
+size_t lml_smem_bytes(bool grad);
 
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
 struct CovParams {

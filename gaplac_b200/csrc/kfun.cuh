@@ -5,6 +5,7 @@
 // src/abstractgp_translations.jl:8-15 and src/gp_parts.jl:11-13.  Nothing is materialised per node: each
 // thread evaluates sum_t coef_t prod_f leaf_f for its own R x C block of entries, in registers.
 #pragma once
+#include "fastexp.h"
 #include "program.h"
 
 namespace gpl {
@@ -13,7 +14,10 @@ namespace gpl {
 struct ItemScalars {
     double a[GPL_MAX_FACTORS];   // SQEXP: -1/(2 l^2); OU: -1/l; LINEAR: c; PARAM: theta
     double da[GPL_MAX_FACTORS];  // derivative scale: SQEXP 1/l^3 (dk = k d^2 / l^3); OU 1/l^2 (dk = k |d| / l^2)
+    double etab[64];             // 2^(j/64) for fast_exp (fastexp.h), copied from constant memory once per CTA
 };
+
+static __constant__ double c_exptab[64] = {GPL_EXP_TABLE_VALUES};
 
 __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const double *__restrict__ theta,
                                                      ItemScalars *S, int tid) {
@@ -31,6 +35,7 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
         S->a[tid] = a;
         S->da[tid] = da;
     }
+    if (tid >= 64 && tid < 128) S->etab[tid - 64] = c_exptab[tid - 64];
 }
 
 // leaf value for one pair; `same_idx` = the two row indices are the same observation (Noise only)
@@ -122,13 +127,13 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             double d = xi[r] - xj[c];
-                            prod[r][c] *= exp(a * (d * d));
+                            prod[r][c] *= fast_exp(a * (d * d), S.etab);
                         }
                 } else if (kind == F_OU) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] *= exp(a * fabs(xi[r] - xj[c]));
+                        for (int c = 0; c < C; ++c) prod[r][c] *= fast_exp(a * fabs(xi[r] - xj[c]), S.etab);
                 } else if (kind == F_LINEAR) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
@@ -159,6 +164,26 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
                 out[r][c] = 0.0;
             }
         }
+}
+
+// 2 x 8 block as two 2 x 4 halves: halves the live temporaries (needed to fit 3 CTAs of 256 threads per SM)
+template <bool SAME>
+__device__ __forceinline__ void eval_block_2x8(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
+                                               int lda, int na, const int (&gi)[2], const double *__restrict__ Xb,
+                                               int ldb, int nb, const int (&gj)[8], double diag_add,
+                                               double (&out)[2][8]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int gjh[4];
+        double o[2][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gjh[c] = gj[4 * h + c];
+        eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[r][4 * h + c] = o[r][c];
+    }
 }
 
 // Contract a weight block w[r][c] with dK/dtheta_s for every slot s:  g[s] += sum_rc w[r][c] dK[r][c]/dtheta_s.

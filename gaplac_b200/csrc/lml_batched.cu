@@ -8,7 +8,7 @@
 //
 // Algorithm (per item): left-looking blocked Cholesky on 64 x 64 tiles.  K never exists in memory: tile (i, j)
 // is generated in registers from the input columns and the hyperparameters, updated with the previously
-// factored tiles streamed (double-buffered cp.async half-tiles) from the CTA's private workspace, then
+// factored tiles streamed (double-buffered cp.async stages of 16 columns) from the CTA's private workspace, then
 // factored (diagonal tile, tile_potrf_inv) or multiplied by the inverse of the diagonal tile (tiles below).
 // All contractions run on the FP64 tensor-core path (DMMA, tile.cuh).  The forward solve z = L^-1 y and logdet
 // ride along with the diagonal tiles.  The gradient phase forms M = L^-1 and K^-1 tile by tile and contracts
@@ -23,10 +23,16 @@ namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
+// Shared memory of one CTA.  The 32 KiB staging buffer S holds, in turn: the two 16-column pipeline stages of the
+// row operand (S[0], S[1024]) and of the column operand (S[2048], S[3072]) during the update loop; the
+// factorisation scratch of the diagonal tile; the staged T tile of the triangular solve; one whole tile for the
+// single-buffered alpha / gradient phases.  Only the gradient kernel carries a second whole-tile buffer (Bt),
+// so the plain log-likelihood kernel fits three CTAs per SM (72 KiB each) and the gradient kernel two.
+template <bool GRAD>
 struct __align__(16) LmlSmem {
-    double A[TILE_ELEMS];   // staging: two half-tile stages of the row operand; factorisation scratch (with Bt)
-    double Bt[TILE_ELEMS];  // staging: two half-tile stages of the column operand
-    double W[TILE_ELEMS];   // inverse of the current diagonal tile
+    double S[TILE_ELEMS];
+    double W[TILE_ELEMS];  // inverse of the current diagonal tile
+    double Bt[GRAD ? TILE_ELEMS : 2];
     ItemScalars sc;
     double rsbuf[16];
     double pivbuf[TS];
@@ -49,9 +55,10 @@ __device__ __forceinline__ void block_indices(const TMap &tm, int i, int j, int 
 
 }  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
+template <bool GRAD>
+__device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    LmlSmem &sm = *reinterpret_cast<LmlSmem *>(smem_raw);
+    LmlSmem<GRAD> &sm = *reinterpret_cast<LmlSmem<GRAD> *>(smem_raw);
     const DevProgram &P = prm.prog;
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
@@ -85,44 +92,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
                 const bool diag = (i == j);
-                const int Q = 2 * j;  // half-steps q: tile k = q >> 1, columns 32 (q & 1) .. of L_ik / L_jk
+                const int Q = (TS / KC) * j;  // pipeline steps: 16 columns of L_ik / L_jk each, k = 0..j-1
                 const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1) are contiguous
                 const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;
-                // all readers of the staging buffers (previous tile) are done: start the first loads, then
+                // all readers of the staging buffer (previous tile) are done: start the first loads, then
                 // generate the covariance tile while they are in flight
                 __syncthreads();
                 if (Q > 0) {
-                    half_tile_load_async(sm.A, srcA, tid);
-                    if (!diag) half_tile_load_async(sm.Bt, srcB, tid);
+                    chunk_load_async(sm.S, srcA, tid);
+                    if (!diag) chunk_load_async(sm.S + 2 * CHUNK_ELEMS, srcB, tid);
                     cp_async_commit();
                 }
                 double acc[2][8];
                 {
                     int gi[2], gj[8];
                     block_indices(tm, i, j, gi, gj);
-                    eval_block<2, 8, true>(P, sm.sc, X, n, n, gi, X, n, n, gj, diag_add, acc);
+                    eval_block_2x8<true>(P, sm.sc, X, n, n, gi, X, n, n, gj, diag_add, acc);
                 }
                 double ytmp = 0.0;
                 if (diag && tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
                 for (int q = 0; q < Q; ++q) {
                     cp_async_wait<0>();
-                    __syncthreads();  // half-step q landed for everyone; everyone finished half-step q-1
+                    __syncthreads();  // step q landed for everyone; everyone finished step q-1
                     if (q + 1 < Q) {
-                        const int nb = ((q + 1) & 1) * (TILE_ELEMS / 2);
-                        half_tile_load_async(sm.A + nb, srcA + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
-                        if (!diag) half_tile_load_async(sm.Bt + nb, srcB + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+                        const int nb = ((q + 1) & 1) * CHUNK_ELEMS;
+                        chunk_load_async(sm.S + nb, srcA + (size_t)(q + 1) * CHUNK_ELEMS, tid);
+                        if (!diag) chunk_load_async(sm.S + 2 * CHUNK_ELEMS + nb, srcB + (size_t)(q + 1) * CHUNK_ELEMS, tid);
                         cp_async_commit();
                     }
-                    // a half-tile is 32 whole columns, so it is itself in tile format (the swizzle depends on c & 3)
-                    const double *a = sm.A + (q & 1) * (TILE_ELEMS / 2);
-                    const double *bt = diag ? a : sm.Bt + (q & 1) * (TILE_ELEMS / 2);
-                    tile_mma<true>(acc, a, bt, tm, 0, TS / 2);
-                    if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * (TS / 2), tid, 0, TS / 2);
+                    // 16 whole columns starting at a multiple of 4 are themselves in tile format (swizzle uses c & 3)
+                    const double *a = sm.S + (q & 1) * CHUNK_ELEMS;
+                    const double *bt = diag ? a : a + 2 * CHUNK_ELEMS;
+                    tile_mma<true>(acc, a, bt, tm, 0, KC);
+                    if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * KC, tid, 0, KC);
                 }
                 if (diag) {
                     __syncthreads();  // the staging buffers become the factorisation scratch
                     double w[2][8];
-                    const int fail = tile_potrf_inv(acc, w, tm, sm.A, sm.L16s, sm.W16s, sm.rsbuf, sm.pivbuf, tid);
+                    const int fail = tile_potrf_inv(acc, w, tm, sm.S, sm.L16s, sm.W16s, sm.rsbuf, sm.pivbuf, tid);
                     if (tid == 0 && fail >= 0 && sm.info == 0) sm.info = j * TS + fail + 1;
                     acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
                     acc_to_tile(sm.W, w, tm);
@@ -139,11 +146,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
                 } else {
                     // L_ij = T_ij W_jj'  (W lower triangular: k < c0 + 32 for this warp's columns)
                     __syncthreads();
-                    acc_to_tile(sm.A, acc, tm);
+                    acc_to_tile(sm.S, acc, tm);
                     __syncthreads();
                     double x[2][8];
                     acc_zero(x);
-                    tile_mma<false>(x, sm.A, sm.W, tm, 0, tm.c0 + 32);
+                    tile_mma<false>(x, sm.S, sm.W, tm, 0, tm.c0 + 32);
                     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, x, tm);
                 }
             }
@@ -172,28 +179,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
             if (tid < TS) rj = wsZ[j * TS + tid];
             for (int i = nt - 1; i > j; --i) {
                 __syncthreads();
-                tile_load_async(sm.A, wsL + tri_index(i, j) * TILE_ELEMS, tid);
+                tile_load_async(sm.S, wsL + tri_index(i, j) * TILE_ELEMS, tid);
                 cp_async_commit();
                 cp_async_wait<0>();
                 if (tid < TS) sm.ybuf[tid] = wsAl[i * TS + tid];
                 __syncthreads();
-                if (tid < TS) rj -= tile_col_dot(sm.A, sm.ybuf, tid);
+                if (tid < TS) rj -= tile_col_dot(sm.S, sm.ybuf, tid);
             }
             __syncthreads();
-            tile_load_async(sm.A, wsW + (size_t)j * TILE_ELEMS, tid);
+            tile_load_async(sm.S, wsW + (size_t)j * TILE_ELEMS, tid);
             cp_async_commit();
             cp_async_wait<0>();
             if (tid < TS) sm.ybuf[tid] = rj;
             __syncthreads();
             if (tid < TS) {
-                const double a = tile_col_dot(sm.A, sm.ybuf, tid);  // W upper part is zero
+                const double a = tile_col_dot(sm.S, sm.ybuf, tid);  // W upper part is zero
                 wsAl[j * TS + tid] = a;
                 if (prm.dy && j * TS + tid < n) prm.dy[(size_t)b * n + j * TS + tid] = info ? NAN : -a;
             }
         }
         __syncthreads();
-        if (!prm.want_grad) continue;
+        if (!GRAD || !prm.want_grad) continue;
 
+        if constexpr (GRAD) {
         // ------------------------------------------------------------------ M = L^-1, stored as M' tiles ----
         // M_jj = W_jj ; M_ij = -W_ii * sum_{k=j}^{i-1} L_ik M_kj  (i > j).  wsM holds the TRANSPOSE of every tile of
         // M, so that M_kj can be the column operand of C += A B' (B'(k, n) = M_kj(k, n)).
@@ -202,34 +210,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
                 double acc[2][8];
                 if (i == j) {
                     __syncthreads();
-                    tile_load_async(sm.A, wsW + (size_t)j * TILE_ELEMS, tid);
+                    tile_load_async(sm.S, wsW + (size_t)j * TILE_ELEMS, tid);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    acc_from_tile(acc, sm.A, tm);
+                    acc_from_tile(acc, sm.S, tm);
                     acc_to_tile_t(wsM + tri_index(j, j) * TILE_ELEMS, acc, tm);
                     continue;
                 }
                 acc_zero(acc);
                 for (int k = j; k < i; ++k) {
                     __syncthreads();
-                    tile_load_async(sm.A, wsL + tri_index(i, k) * TILE_ELEMS, tid);
+                    tile_load_async(sm.S, wsL + tri_index(i, k) * TILE_ELEMS, tid);
                     tile_load_async(sm.Bt, wsM + tri_index(k, j) * TILE_ELEMS, tid);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    tile_mma<false>(acc, sm.A, sm.Bt, tm, 0, TS);  // S += L_ik M_kj
+                    tile_mma<false>(acc, sm.S, sm.Bt, tm, 0, TS);  // S += L_ik M_kj
                 }
                 // M_ij = -W_ii S : row operand W_ii, column operand S' (transposed store of the accumulator)
                 __syncthreads();
-                tile_load_async(sm.A, wsW + (size_t)i * TILE_ELEMS, tid);
+                tile_load_async(sm.S, wsW + (size_t)i * TILE_ELEMS, tid);
                 cp_async_commit();
                 acc_to_tile_t(sm.Bt, acc, tm);
                 cp_async_wait<0>();
                 __syncthreads();
                 double mij[2][8];
                 acc_zero(mij);
-                tile_mma<true>(mij, sm.A, sm.Bt, tm, 0, TS);
+                tile_mma<true>(mij, sm.S, sm.Bt, tm, 0, TS);
                 acc_to_tile_t(wsM + tri_index(i, j) * TILE_ELEMS, mij, tm);
             }
         }
@@ -243,12 +251,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
                 acc_zero(acc);
                 for (int k = i; k < nt; ++k) {
                     __syncthreads();
-                    tile_load_async(sm.A, wsM + tri_index(k, i) * TILE_ELEMS, tid);
+                    tile_load_async(sm.S, wsM + tri_index(k, i) * TILE_ELEMS, tid);
                     if (i != j) tile_load_async(sm.Bt, wsM + tri_index(k, j) * TILE_ELEMS, tid);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    tile_mma<false>(acc, sm.A, (i == j) ? sm.A : sm.Bt, tm, 0, TS);
+                    tile_mma<false>(acc, sm.S, (i == j) ? sm.S : sm.Bt, tm, 0, TS);
                 }
                 int gi[2], gj[8];
                 block_indices(tm, i, j, gi, gj);
@@ -262,9 +270,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_kernel(const __grid_c
         }
         __syncthreads();
         if (tid < prm.p) prm.dtheta[(size_t)b * prm.p + tid] = info ? NAN : -0.5 * sm.gsum[tid];
+        }  // GRAD
     }
 }
 
-size_t lml_smem_bytes() { return sizeof(LmlSmem); }
+__global__ void __launch_bounds__(NTHREADS, 3) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
+    lml_batched_body<false>(prm);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_grad_kernel(const __grid_constant__ LmlParams prm) {
+    lml_batched_body<true>(prm);
+}
+
+size_t lml_smem_bytes(bool grad) { return grad ? sizeof(LmlSmem<true>) : sizeof(LmlSmem<false>); }
 
 }  // namespace gpl

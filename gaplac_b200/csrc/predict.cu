@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
             double acc[2][8];
-            eval_block<2, 8, false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
+            eval_block_2x8<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
                 const double al = gi[mb] < n ? prm.alpha[gi[mb]] : 0.0;

@@ -77,6 +77,12 @@ __device__ __forceinline__ void tile_load_async(double *smem, const double *__re
 __device__ __forceinline__ void half_tile_load_async(double *smem, const double *__restrict__ gmem, int tid) {
     block_load_async<TILE_BYTES / 2>(smem, gmem, tid);
 }
+// 16 whole columns of a tile (8 KiB): the pipeline stage of the factorisation kernels
+constexpr int KC = 16;
+constexpr int CHUNK_ELEMS = KC * TS;
+__device__ __forceinline__ void chunk_load_async(double *smem, const double *__restrict__ gmem, int tid) {
+    block_load_async<CHUNK_ELEMS * 8>(smem, gmem, tid);
+}
 
 __device__ __forceinline__ void tile_store(double *__restrict__ gmem, const double *smem, int tid) {
 #pragma unroll
@@ -179,7 +185,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][8], const double *__re
 //   4. all warps apply the rank-16 update to their register blocks of the trailing tile and of the inverse (DMMA).
 // Three block barriers per panel.  The inverse rides along as a block Gauss-Jordan on the identity, so the
 // triangular solves of the tiles below (L_ij = T_ij L_jj^-T) become plain GEMMs.
-// scratch: 8192 doubles (two ping-pong sets of P, R, Lp, Rp, each 64 x 16 in tile format);
+// scratch: 4096 doubles (P, R, Lp, Rp, each 64 x 16 in tile format; the three barriers order every reuse);
 // L16s / W16s: 256 doubles each; rsbuf: 16; pivbuf: 64 (pivots, for logdet).
 // Returns (in warp 0) -1 or the local index of the first non-positive pivot.
 template <int P_>
@@ -187,7 +193,7 @@ __device__ __forceinline__ void potrf_panel(double (&acc)[2][8], double (&w)[2][
                                             double *L16s, double *W16s, double *rsbuf, double *pivbuf, int tid,
                                             int &fail) {
     const int warp = tid >> 5, lane = tid & 31, wr = warp >> 1, wc = warp & 1;
-    double *P = scratch + (P_ & 1) * 4096;  // tile columns 16 P_.. of the tile:  element (row, k) at tidx(row, k)
+    double *P = scratch;                    // tile columns 16 P_.. of the tile:  element (row, k) at tidx(row, k)
     double *R = P + 1024;                   // rows 16 P_.. of the inverse, as (col, k):  tidx(col, k)
     double *Lp = P + 2048;                  // panel of L, (row, k)
     double *Rp = P + 3072;                  // new rows of the inverse, (col, k)
