@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgaplac_b200.so")
+LIB_PATH = os.environ.get("GAPLAC_B200_LIB", os.path.join(_HERE, "libgaplac_b200.so"))  # env: experiment builds
 
 GPL_OK, GPL_ERR_ARG, GPL_ERR_CUDA, GPL_ERR_LIMIT, GPL_ERR_NOTPD = 0, -1, -2, -3, -4
 SQEXP, OU, LINEAR, CAT, CONSTANT, NOISE, ADD, MUL = range(8)

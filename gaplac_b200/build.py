@@ -42,6 +42,23 @@ def _compile(src: str, force: bool, hdr_time: float) -> tuple[str, bool]:
     return obj, True
 
 
+def build_variant(tag: str, defs: list[str]) -> str:
+    """Experiment builds: libgaplac_b200_<tag>.so with extra -D flags (select with GAPLAC_B200_LIB=<path>)."""
+    obj_dir = os.path.join(OBJ, tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for src in CU_SOURCES + CPP_SOURCES:
+        path, obj = os.path.join(CSRC, src), os.path.join(obj_dir, src + ".o")
+        if src.endswith(".cu"):
+            subprocess.check_call(["nvcc", *NVCC_FLAGS, *defs, "-c", path, "-o", obj])
+        else:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-c", path, "-o", obj])
+        objs.append(obj)
+    lib = os.path.join(HERE, f"libgaplac_b200_{tag}.so")
+    subprocess.check_call(["nvcc", "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdr_time = _newest_header()

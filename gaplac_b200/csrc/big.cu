@@ -18,7 +18,7 @@ struct __align__(16) BigSmem {
     double A[TILE_ELEMS];
     double Bt[TILE_ELEMS];
     double W[TILE_ELEMS];
-    double rsbuf[16];
+    double rsbuf[32];
     double pivbuf[TS];
     double ybuf[TS];
     double L16s[256];

@@ -34,8 +34,8 @@ namespace gpl {
         0x1.d072d4a07897cp+0, 0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,  \
         0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0
 
-GPL_HD double fast_exp(double x, const double *__restrict__ tab) {
-    if (!(fabs(x) <= 700.0)) return exp(x);  // NaN, huge, deep underflow: the general path
+// branch-free core: valid for |x| <= 700 (no range check, no special values)
+GPL_HD double fast_exp_core(double x, const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer in the low bits
     const double t = fma(x, 0x1.71547652b82fep+6, MAGIC);
     const double tn = t - MAGIC;
@@ -67,6 +67,37 @@ GPL_HD double fast_exp(double x, const double *__restrict__ tab) {
     memcpy(&out, &vb, 8);
     return out;
 #endif
+}
+
+#ifdef __CUDACC__
+static __device__ __noinline__ double exp_general(double x) { return exp(x); }  // out of line: keeps the hot code small
+#endif
+
+GPL_HD double fast_exp(double x, const double *__restrict__ tab) {
+#ifdef __CUDA_ARCH__
+    if (!(fabs(x) <= 700.0)) return exp_general(x);  // NaN, huge, deep underflow: the general path
+#else
+    if (!(fabs(x) <= 700.0)) return exp(x);
+#endif
+    return fast_exp_core(x, tab);
+}
+
+// N independent evaluations with ONE range check for the group: the N dependency chains interleave (the scalar
+// version's per-call branch kept them serial, which left the covariance tiles latency-bound: profiles/ README).
+template <int N>
+GPL_HD void fast_exp_vec(double (&x)[N], const double *__restrict__ tab) {
+    double mx = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && (fabs(x[i]) <= 700.0);  // false for NaN
+    (void)mx;
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = fast_exp_core(x[i], tab);
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) x[i] = fast_exp(x[i], tab);
+    }
 }
 
 }  // namespace gpl

@@ -121,19 +121,20 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
                 for (int r = 0; r < R; ++r) xi[r] = Xa[(size_t)col * lda + ci[r]];
 #pragma unroll
                 for (int c = 0; c < C; ++c) xj[c] = Xb[(size_t)col * ldb + cj[c]];
-                if (kind == F_SQEXP) {
+                if (kind == F_SQEXP || kind == F_OU) {
+                    double e[R * C];
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            double d = xi[r] - xj[c];
-                            prod[r][c] *= fast_exp(a * (d * d), S.etab);
+                            const double d = xi[r] - xj[c];
+                            e[r * C + c] = a * (kind == F_SQEXP ? d * d : fabs(d));
                         }
-                } else if (kind == F_OU) {
+                    fast_exp_vec<R * C>(e, S.etab);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] *= fast_exp(a * fabs(xi[r] - xj[c]), S.etab);
+                        for (int c = 0; c < C; ++c) prod[r][c] *= e[r * C + c];
                 } else if (kind == F_LINEAR) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
@@ -172,17 +173,20 @@ __device__ __forceinline__ void eval_block_2x8(const DevProgram &P, const ItemSc
                                                int lda, int na, const int (&gi)[2], const double *__restrict__ Xb,
                                                int ldb, int nb, const int (&gj)[8], double diag_add,
                                                double (&out)[2][8]) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {  // rolled: one copy of the evaluation code
         int gjh[4];
         double o[2][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gjh[c] = gj[4 * h + c];
+        for (int c = 0; c < 4; ++c) gjh[c] = h ? gj[4 + c] : gj[c];
         eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) out[r][4 * h + c] = o[r][c];
+            for (int c = 0; c < 4; ++c) {
+                if (h) out[r][4 + c] = o[r][c];
+                else out[r][c] = o[r][c];
+            }
     }
 }
 

@@ -21,20 +21,30 @@ namespace gpl {
 
 namespace {
 
+#ifndef GPL_LML_CTAS_PER_SM
+#define GPL_LML_CTAS_PER_SM 2
+#endif
+#ifndef GPL_LML_KC
+#define GPL_LML_KC 32  // columns per pipeline stage (two stages of row + column operand = KC * 2 KiB)
+#endif
+constexpr int LKC = GPL_LML_KC;
+constexpr int LCH = LKC * TS;  // doubles per operand stage
+static_assert(4 * LCH <= 2 * TILE_ELEMS, "stages must fit the staging buffer");
+
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
-// Shared memory of one CTA.  The 32 KiB staging buffer S holds, in turn: the two 16-column pipeline stages of the
-// row operand (S[0], S[1024]) and of the column operand (S[2048], S[3072]) during the update loop; the
+// Shared memory of one CTA.  The staging buffer S holds, in turn: the two LKC-column pipeline stages of the row
+// operand (S[0], S[LCH]) and of the column operand (S[2 LCH], S[3 LCH]) during the update loop; the
 // factorisation scratch of the diagonal tile; the staged T tile of the triangular solve; one whole tile for the
 // single-buffered alpha / gradient phases.  Only the gradient kernel carries a second whole-tile buffer (Bt),
 // so the plain log-likelihood kernel fits three CTAs per SM (72 KiB each) and the gradient kernel two.
 template <bool GRAD>
 struct __align__(16) LmlSmem {
-    double S[TILE_ELEMS];
+    double S[4 * LCH > TILE_ELEMS ? 4 * LCH : TILE_ELEMS];
     double W[TILE_ELEMS];  // inverse of the current diagonal tile
     double Bt[GRAD ? TILE_ELEMS : 2];
     ItemScalars sc;
-    double rsbuf[16];
+    double rsbuf[32];
     double pivbuf[TS];
     double ybuf[TS];
     double L16s[256];
@@ -92,15 +102,15 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
                 const bool diag = (i == j);
-                const int Q = (TS / KC) * j;  // pipeline steps: 16 columns of L_ik / L_jk each, k = 0..j-1
+                const int Q = (TS / LKC) * j;  // pipeline steps: LKC columns of L_ik / L_jk each, k = 0..j-1
                 const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1) are contiguous
                 const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;
                 // all readers of the staging buffer (previous tile) are done: start the first loads, then
                 // generate the covariance tile while they are in flight
                 __syncthreads();
                 if (Q > 0) {
-                    chunk_load_async(sm.S, srcA, tid);
-                    if (!diag) chunk_load_async(sm.S + 2 * CHUNK_ELEMS, srcB, tid);
+                    block_load_async<LCH * 8>(sm.S, srcA, tid);
+                    if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH, srcB, tid);
                     cp_async_commit();
                 }
                 double acc[2][8];
@@ -115,16 +125,16 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                     cp_async_wait<0>();
                     __syncthreads();  // step q landed for everyone; everyone finished step q-1
                     if (q + 1 < Q) {
-                        const int nb = ((q + 1) & 1) * CHUNK_ELEMS;
-                        chunk_load_async(sm.S + nb, srcA + (size_t)(q + 1) * CHUNK_ELEMS, tid);
-                        if (!diag) chunk_load_async(sm.S + 2 * CHUNK_ELEMS + nb, srcB + (size_t)(q + 1) * CHUNK_ELEMS, tid);
+                        const int nb = ((q + 1) & 1) * LCH;
+                        block_load_async<LCH * 8>(sm.S + nb, srcA + (size_t)(q + 1) * LCH, tid);
+                        if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH + nb, srcB + (size_t)(q + 1) * LCH, tid);
                         cp_async_commit();
                     }
                     // 16 whole columns starting at a multiple of 4 are themselves in tile format (swizzle uses c & 3)
-                    const double *a = sm.S + (q & 1) * CHUNK_ELEMS;
-                    const double *bt = diag ? a : a + 2 * CHUNK_ELEMS;
-                    tile_mma<true>(acc, a, bt, tm, 0, KC);
-                    if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * KC, tid, 0, KC);
+                    const double *a = sm.S + (q & 1) * LCH;
+                    const double *bt = diag ? a : a + 2 * LCH;
+                    tile_mma<true>(acc, a, bt, tm, 0, LKC);
+                    if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * LKC, tid, 0, LKC);
                 }
                 if (diag) {
                     __syncthreads();  // the staging buffers become the factorisation scratch
@@ -274,7 +284,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 3) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
+__global__ void __launch_bounds__(NTHREADS, GPL_LML_CTAS_PER_SM) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
     lml_batched_body<false>(prm);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) lml_batched_grad_kernel(const __grid_constant__ LmlParams prm) {

@@ -177,7 +177,8 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][8], const double *__re
 
 // ---- Cholesky of the diagonal tile with its inverse, blocked ---------------------------------------------------
 // In: acc = the 64 x 64 SPD tile (lower part used).  Out: acc = L (zeros above the diagonal), w = L^-1.
-// The tile is processed in four 16-column panels:
+// The tile is processed in four 16-column panels (a rolled loop: the whole routine is ~20 KiB of SASS; the first,
+// fully unrolled version was 270 KiB and made instruction fetch the second largest stall of the kernel):
 //   1. the owners of the panel's columns (acc) and of the panel's rows of the running inverse (w) publish them;
 //   2. warp 0 factors the 16 x 16 diagonal block in registers (one row per lane, pivots and columns exchanged
 //      with warp shuffles: no block barrier inside) and inverts it by forward substitution;
@@ -186,159 +187,151 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][8], const double *__re
 // Three block barriers per panel.  The inverse rides along as a block Gauss-Jordan on the identity, so the
 // triangular solves of the tiles below (L_ij = T_ij L_jj^-T) become plain GEMMs.
 // scratch: 4096 doubles (P, R, Lp, Rp, each 64 x 16 in tile format; the three barriers order every reuse);
-// L16s / W16s: 256 doubles each; rsbuf: 16; pivbuf: 64 (pivots, for logdet).
+// L16s / W16s: 256 doubles each; rsbuf: 16 + 16 (reciprocal pivots, pivot-column exchange); pivbuf: 64 (pivots).
 // Returns (in warp 0) -1 or the local index of the first non-positive pivot.
-template <int P_>
-__device__ __forceinline__ void potrf_panel(double (&acc)[2][8], double (&w)[2][8], const TMap &tm, double *scratch,
-                                            double *L16s, double *W16s, double *rsbuf, double *pivbuf, int tid,
-                                            int &fail) {
+__device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2][8], const TMap &tm, double *scratch,
+                                           double *L16s, double *W16s, double *rsbuf, double *pivbuf, int tid) {
     const int warp = tid >> 5, lane = tid & 31, wr = warp >> 1, wc = warp & 1;
-    double *P = scratch;                    // tile columns 16 P_.. of the tile:  element (row, k) at tidx(row, k)
-    double *R = P + 1024;                   // rows 16 P_.. of the inverse, as (col, k):  tidx(col, k)
-    double *Lp = P + 2048;                  // panel of L, (row, k)
-    double *Rp = P + 3072;                  // new rows of the inverse, (col, k)
-    // 1. publish
-    if (wc == (P_ >> 1)) {
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cc = (P_ & 1) * 4 + q;
-                P[tidx(row_of(tm, mb), col_of(tm, cc) - 16 * P_)] = acc[mb][cc];
-            }
-    }
-    if (wr == P_) {
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) R[tidx(col_of(tm, cc), row_of(tm, mb) - 16 * P_)] = w[mb][cc];
-    }
-    __syncthreads();
-    // 2. warp 0: 16 x 16 Cholesky (row per lane) and inverse
-    if (warp == 0) {
-        const int r = lane & 15;
-        double a[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) a[c] = P[tidx(16 * P_ + r, c)];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            double piv = __shfl_sync(0xffffffffu, a[c], c);
-            if (!(piv > 0.0)) {
-                if (fail < 0) fail = 16 * P_ + c;
-                piv = 1.0;
-            }
-            const double rs = rsqrt(piv);
-            if (lane == 0) {
-                pivbuf[16 * P_ + c] = piv;
-                rsbuf[c] = rs;
-            }
-            const double l = a[c] * rs;
-            a[c] = (r >= c) ? l : 0.0;
-#pragma unroll
-            for (int c2 = c + 1; c2 < 16; ++c2) {
-                const double l2 = __shfl_sync(0xffffffffu, l, c2);
-                a[c2] = fma(-l, l2, a[c2]);
-            }
-        }
-        if (lane < 16) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) L16s[c * 16 + r] = a[c];  // L16[r][c], column-major
-        }
-        __syncwarp();
-        double x[16];  // column r of L16^-1 (axpy-form forward substitution)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = (i == r) ? 1.0 : 0.0;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            x[c] *= rsbuf[c];
-#pragma unroll
-            for (int i = c + 1; i < 16; ++i) x[i] = fma(-L16s[c * 16 + i], x[c], x[i]);
-        }
-        if (lane < 16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) W16s[i * 16 + r] = x[i];  // W16[i][r], row-major
-        }
-    }
-    __syncthreads();
-    // 3a. Lp: rows below the block = P * W16', rows of the block = L16, rows above = 0
-    {
-        const int row = tid & 63, cg = tid >> 6;
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (row >= 16 * (P_ + 1)) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const double pk = P[tidx(row, k)];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = 4 * cg + q;
-                    if (k <= c) out[q] = fma(pk, W16s[c * 16 + k], out[q]);
-                }
-            }
-        } else if (row >= 16 * P_) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) out[q] = L16s[(4 * cg + q) * 16 + (row - 16 * P_)];
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) Lp[tidx(row, 4 * cg + q)] = out[q];
-    }
-    // 3b. Rp = W16 * R   (element (col, k) <- sum_{k2 <= k} W16[k][k2] R(col, k2))
-    {
-        const int col = tid & 63, kg = tid >> 6;
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) {
-            const double rv = R[tidx(col, k2)];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = 4 * kg + q;
-                if (k2 <= k) out[q] = fma(W16s[k * 16 + k2], rv, out[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) Rp[tidx(col, 4 * kg + q)] = out[q];
-    }
-    __syncthreads();
-    // 4. register-block updates.  Column half h (n-blocks 2h, 2h+1) of this warp belongs to panel pc = 2 wc + h.
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int pc = 2 * wc + h;
-        if (pc == P_) {  // finished columns of L
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    acc[mb][4 * h + q] = Lp[tidx(row_of(tm, mb), col_of(tm, 4 * h + q) - 16 * P_)];
-        } else if (pc > P_ && wr >= pc) {  // trailing lower part: T -= Lp Lp'
-            if (h == 0) tile_mma<true, 0x3>(acc, Lp, Lp, tm, 0, 16);
-            else tile_mma<true, 0xC>(acc, Lp, Lp, tm, 0, 16);
-        }
-        if (pc <= P_) {  // inverse: only columns <= the panel are non-zero in the new rows
-            if (wr > P_) {
-                if (h == 0) tile_mma<true, 0x3>(w, Lp, Rp, tm, 0, 16);
-                else tile_mma<true, 0xC>(w, Lp, Rp, tm, 0, 16);
-            } else if (wr == P_) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        w[mb][4 * h + q] = Rp[tidx(col_of(tm, 4 * h + q), row_of(tm, mb) - 16 * P_)];
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2][8], const TMap &tm,
-                                              double *scratch, double *L16s, double *W16s, double *rsbuf,
-                                              double *pivbuf, int tid) {
+    double *P = scratch;         // columns of the panel:           element (row, k) at tidx(row, k)
+    double *R = P + 1024;        // rows of the inverse, as (col, k): tidx(col, k)
+    double *Lp = P + 2048;       // panel of L, (row, k)
+    double *Rp = P + 3072;       // new rows of the inverse, (col, k)
+    double *colx = rsbuf + 16;   // pivot-column exchange of warp 0
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) w[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
     int fail = -1;
-    potrf_panel<0>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
-    potrf_panel<1>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
-    potrf_panel<2>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
-    potrf_panel<3>(acc, w, tm, scratch, L16s, W16s, rsbuf, pivbuf, tid, fail);
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        const int hs = p & 1;  // which column half of the owning warps holds the panel
+        // 1. publish
+        if (wc == (p >> 1)) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    P[tidx(row_of(tm, mb), col_of(tm, q) - tm.c0)] = hs ? acc[mb][4 + q] : acc[mb][q];  // panel-local column
+        }
+        if (wr == p) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) R[tidx(col_of(tm, cc), 8 * mb + tm.g)] = w[mb][cc];
+        }
+        __syncthreads();
+        // 2. warp 0: 16 x 16 Cholesky, one row per lane, pivots and columns exchanged with warp shuffles
+        if (warp == 0) {
+            const int c_own = lane & 15;  // row owned by this lane (lanes 16..31 mirror 0..15)
+            double a[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a[c] = P[tidx(16 * p + c_own, c)];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0)) {
+                    if (fail < 0) fail = 16 * p + c;
+                    piv = 1.0;
+                }
+                const double rs = rsqrt(piv);
+                if (lane == 0) {
+                    pivbuf[16 * p + c] = piv;
+                    rsbuf[c] = rs;
+                }
+                const double l = a[c] * rs;
+                a[c] = (c_own >= c) ? l : 0.0;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 16; ++c2) {
+                    const double l2 = __shfl_sync(0xffffffffu, l, c2);
+                    a[c2] = fma(-l, l2, a[c2]);
+                }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) L16s[c * 16 + c_own] = a[c];  // L16[r][c], column-major
+            }
+            __syncwarp();
+            double x[16];  // column c_own of L16^-1 (axpy-form forward substitution)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = (i == c_own) ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                x[c] *= rsbuf[c];
+#pragma unroll
+                for (int i = c + 1; i < 16; ++i) x[i] = fma(-L16s[c * 16 + i], x[c], x[i]);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) W16s[i * 16 + c_own] = x[i];  // W16[i][c], row-major
+            }
+        }
+        __syncthreads();
+        // 3a. Lp: rows below the block = P * W16', rows of the block = L16, rows above = 0
+        {
+            const int row = tid & 63, cg = tid >> 6;
+            double out[4] = {0.0, 0.0, 0.0, 0.0};
+            if (row >= 16 * (p + 1)) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const double pk = P[tidx(row, k)];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = 4 * cg + q;
+                        if (k <= c) out[q] = fma(pk, W16s[c * 16 + k], out[q]);
+                    }
+                }
+            } else if (row >= 16 * p) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[q] = L16s[(4 * cg + q) * 16 + (row - 16 * p)];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Lp[tidx(row, 4 * cg + q)] = out[q];
+        }
+        // 3b. Rp = W16 * R   (element (col, k) <- sum_{k2 <= k} W16[k][k2] R(col, k2))
+        {
+            const int col = tid & 63, kg = tid >> 6;
+            double out[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                const double rv = R[tidx(col, k2)];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = 4 * kg + q;
+                    if (k2 <= k) out[q] = fma(W16s[k * 16 + k2], rv, out[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Rp[tidx(col, 4 * kg + q)] = out[q];
+        }
+        __syncthreads();
+        // 4. register-block updates.  Column half h (n-blocks 2h, 2h+1) of this warp belongs to panel pc = 2 wc + h.
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pc = 2 * wc + h;
+            if (pc == p) {  // finished columns of L
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        acc[mb][4 * h + q] = Lp[tidx(row_of(tm, mb), col_of(tm, 4 * h + q) - 16 * pc)];
+            } else if (pc > p && wr >= pc) {  // trailing lower part: T -= Lp Lp'
+                if (h == 0) tile_mma<true, 0x3>(acc, Lp, Lp, tm, 0, 16);
+                else tile_mma<true, 0xC>(acc, Lp, Lp, tm, 0, 16);
+            }
+            if (pc <= p) {  // inverse: only columns <= the panel are non-zero in the new rows
+                if (wr > p) {
+                    if (h == 0) tile_mma<true, 0x3>(w, Lp, Rp, tm, 0, 16);
+                    else tile_mma<true, 0xC>(w, Lp, Rp, tm, 0, 16);
+                } else if (wr == p) {
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            w[mb][4 * h + q] = Rp[tidx(col_of(tm, 4 * h + q), 8 * mb + tm.g)];
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
