@@ -182,7 +182,8 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     if (!attr_set) {
         CU(ctx, cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(ctx, cudaFuncSetAttribute(big_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(ctx, cudaFuncSetAttribute(big_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)big_trail_smem_bytes()));
         attr_set = true;
     }
     CU(ctx, cudaMemsetAsync(dinfo, 0, sizeof(int), st));
@@ -208,7 +209,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         }
         if (j1 < nt) {
             const long long ntrail = tri_index(nt - j1, 0);
-            big_trail_kernel<<<(unsigned)ntrail, NTHREADS, smem, st>>>(prm);
+            big_trail_kernel<<<(unsigned)ntrail, NTHREADS, big_trail_smem_bytes(), st>>>(prm);
             ctx->launches++;
         }
     }

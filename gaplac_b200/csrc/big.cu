@@ -4,7 +4,7 @@
 // Replaces cholesky(Symmetric(K_y)) -> dpotrf('U') + U' \ y -> dtrtrs + logdet [upstream LinearAlgebra /
 // OpenBLAS via AbstractGPs logpdf / posterior]; call sites CLI/src/select.jl:49-52, src/plotting.jl:8.
 //
-// Two-level blocking.  A panel is PANEL tile columns (256 matrix columns).  Inside a panel the tile columns are
+// Two-level blocking (one CTA of 128 threads per tile, DMMA tile primitives of tile.cuh).  A panel is PANEL tile columns (256 matrix columns).  Inside a panel the tile columns are
 // factored left-looking (big_diag_kernel: 1 CTA; big_col_kernel: one CTA per tile below the diagonal); after
 // a panel, big_trail_kernel applies its rank-256 update to every remaining tile (one CTA per tile, K = 256 so
 // the trailing matrix moves through HBM once per panel, not once per tile column).
@@ -18,11 +18,11 @@ struct __align__(16) BigSmem {
     double A[TILE_ELEMS];
     double Bt[TILE_ELEMS];
     double W[TILE_ELEMS];
-    double rsbuf[32];
+    double D[DSIZE];
+    double rsbuf[16];
     double pivbuf[TS];
     double ybuf[TS];
     double L16s[256];
-    double W16s[256];
 };
 
 }  // namespace
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NTHREADS) big_diag_kernel(BigParams prm) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[2][8];
+    double acc[2][NCC];
     acc_from_tile(acc, sm.A, tm);
     for (int k = prm.k0; k < j; ++k) {
         __syncthreads();
@@ -93,12 +93,21 @@ __global__ void __launch_bounds__(NTHREADS) big_diag_kernel(BigParams prm) {
         tile_mma<true>(acc, sm.A, sm.A, tm, 0, TS);
     }
     __syncthreads();
-    double w[2][8];
-    const int fail = tile_potrf_inv(acc, w, tm, sm.A, sm.L16s, sm.W16s, sm.rsbuf, sm.pivbuf, tid);
+    const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
     if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
     acc_to_tile(Tjj, acc, tm);
-    acc_to_tile(sm.W, w, tm);
+    __syncthreads();
+    acc_to_tile(sm.A, acc, tm);  // L_jj in shared memory for the inverse
     if (prm.y && tid < TS) sm.ybuf[tid] = prm.y[j * TS + tid];
+    __syncthreads();
+    // full inverse W_jj = L_jj^-1 (X L' = I gives W'): the column kernel and the backward solve use it
+    double e[2][NCC];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+    tile_trsm_ld(e, sm.A, sm.D, tm);
+    acc_to_tile_t(sm.W, e, tm);
     __syncthreads();
     tile_store(prm.winv + (size_t)j * TILE_ELEMS, sm.W, tid);
     if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[2][8];
+    double acc[2][NCC];
     acc_from_tile(acc, sm.A, tm);
     for (int k = prm.k0; k < j; ++k) {
         __syncthreads();
@@ -129,25 +138,21 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
         __syncthreads();
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
-    __syncthreads();
-    acc_to_tile(sm.A, acc, tm);
-    __syncthreads();
-    double x[2][8];
-    acc_zero(x);
-    tile_mma<false>(x, sm.A, sm.W, tm, 0, tm.c0 + 32);
-    acc_to_tile(Tij, x, tm);
+    tile_trsm_w(acc, sm.W, tm);  // L_ij = T_ij W_jj', row operand straight from the accumulator registers
+    acc_to_tile(Tij, acc, tm);
     if (prm.y) {
         __syncthreads();
-        acc_to_tile(sm.A, x, tm);
+        acc_to_tile(sm.A, acc, tm);
         __syncthreads();
         if (tid < TS) prm.y[i * TS + tid] -= tile_row_dot(sm.A, prm.y + j * TS, tid, 0, TS);
     }
 }
 
 // trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'
-__global__ void __launch_bounds__(NTHREADS, 2) big_trail_kernel(BigParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 4) big_trail_kernel(BigParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    double *S = reinterpret_cast<double *>(smem_raw);  // two stages of 16 columns of both operands (32 KiB)
+    constexpr int KC = 16, CH = KC * TS;
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
     int ii, ll;
@@ -155,29 +160,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) big_trail_kernel(BigParams prm) {
     const int i = prm.j1 + ii, l = prm.j1 + ll;
     const bool diag = (i == l);
     double *Til = prm.tiles + tri_index(i, l) * TILE_ELEMS;
-    const int Q = 2 * (prm.j1 - prm.k0);  // half-steps of 32 panel columns; the panel's tiles of a row are contiguous
+    const int Q = (TS / KC) * (prm.j1 - prm.k0);  // the panel's tiles of a tile row are contiguous
     const double *srcA = prm.tiles + tri_index(i, prm.k0) * TILE_ELEMS;
     const double *srcB = prm.tiles + tri_index(l, prm.k0) * TILE_ELEMS;
-    half_tile_load_async(sm.A, srcA, tid);
-    if (!diag) half_tile_load_async(sm.Bt, srcB, tid);
+    block_load_async<CH * 8>(S, srcA, tid);
+    if (!diag) block_load_async<CH * 8>(S + 2 * CH, srcB, tid);
     cp_async_commit();
-    double acc[2][8];
+    double acc[2][NCC];
     acc_from_tile(acc, Til, tm);  // straight from global / L2 into the accumulator registers
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<0>();
         __syncthreads();
         if (q + 1 < Q) {
-            const int nb = ((q + 1) & 1) * (TILE_ELEMS / 2);
-            half_tile_load_async(sm.A + nb, srcA + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
-            if (!diag) half_tile_load_async(sm.Bt + nb, srcB + (size_t)(q + 1) * (TILE_ELEMS / 2), tid);
+            const int nb = ((q + 1) & 1) * CH;
+            block_load_async<CH * 8>(S + nb, srcA + (size_t)(q + 1) * CH, tid);
+            if (!diag) block_load_async<CH * 8>(S + 2 * CH + nb, srcB + (size_t)(q + 1) * CH, tid);
             cp_async_commit();
         }
-        const double *a = sm.A + (q & 1) * (TILE_ELEMS / 2);
-        const double *bt = diag ? a : sm.Bt + (q & 1) * (TILE_ELEMS / 2);
-        tile_mma<true>(acc, a, bt, tm, 0, TS / 2);
+        const double *a = S + (q & 1) * CH;
+        const double *bt = diag ? a : a + 2 * CH;
+        tile_mma<true>(acc, a, bt, tm, 0, KC);
     }
     acc_to_tile(Til, acc, tm);
 }
+size_t big_trail_smem_bytes() { return TILE_BYTES; }
 
 // backward substitution, one launch per tile row i (descending), grid = i + 1: every CTA recomputes
 // alpha_i = W_ii' r_i (r_i is final and read-only in this launch), CTA j < i applies r_j -= L_ij' alpha_i,
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS) big_backward_kernel(const double *ti
 
 __global__ void __launch_bounds__(NTHREADS) big_reduce_kernel(const double *pivlog, const double *z, int len,
                                                               double *out) {
-    __shared__ double red[8];
+    __shared__ double red[NWARPS];
     const int tid = threadIdx.x;
     double ld = 0.0, q = 0.0;
     for (int t = tid; t < len; t += NTHREADS) {

@@ -18,18 +18,20 @@ __global__ void __launch_bounds__(NTHREADS) cov_dense_kernel(const __grid_consta
     prepare_item_scalars(prm.prog, prm.theta, &sc, tid);
     __syncthreads();
     const TMap tm = thread_map(tid);
-    int gi[2], gj[8];
+    int gi[2], gj[NCC];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) gi[mb] = blockIdx.x * TS + row_of(tm, mb);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) gj[cc] = blockIdx.y * TS + col_of(tm, cc);
-    double acc[2][8];
+    for (int cc = 0; cc < NCC; ++cc) gj[cc] = blockIdx.y * TS + col_of(tm, cc);
+    double acc[2][NCC];
     if (prm.same)
-        eval_block_2x8<true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, prm.diag_add, acc);
+        eval_block_acc<true>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, blockIdx.y * TS, tm.t,
+                             prm.diag_add, acc);
     else
-        eval_block_2x8<false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, gj, 0.0, acc);
+        eval_block_acc<false>(prm.prog, sc, prm.Xa, prm.na, prm.na, gi, prm.Xb, prm.nb, prm.nb, blockIdx.y * TS, tm.t, 0.0,
+                              acc);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
+    for (int cc = 0; cc < NCC; ++cc) {
         if (gj[cc] >= prm.nb) continue;
         double *col = prm.K + (size_t)gj[cc] * prm.na;
 #pragma unroll
@@ -48,13 +50,11 @@ __global__ void __launch_bounds__(NTHREADS) cov_tiles_kernel(const __grid_consta
     int i, j;
     tri_unrank(t, i, j);
     const TMap tm = thread_map(tid);
-    int gi[2], gj[8];
+    int gi[2];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) gj[cc] = j * TS + col_of(tm, cc);
-    double acc[2][8];
-    eval_block_2x8<true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, gj, prm.diag_add, acc);
+    double acc[2][NCC];
+    eval_block_acc<true>(prm.prog, sc, prm.X, prm.n, prm.n, gi, prm.X, prm.n, prm.n, j * TS, tm.t, prm.diag_add, acc);
     acc_to_tile(prm.tiles + t * TILE_ELEMS, acc, tm);
 }
 

@@ -70,6 +70,7 @@ __global__ void big_diag_kernel(BigParams prm);   // 1 CTA
 __global__ void big_col_kernel(BigParams prm);    // nt - j - 1 CTAs
 __global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l >= j1)
 size_t big_smem_bytes();
+size_t big_trail_smem_bytes();
 
 // backward substitution alpha = L^-T z, one launch per tile row i (descending), grid = i + 1 CTAs; r = z on entry
 // of the first launch and is updated in place, alpha receives the finished blocks

@@ -167,25 +167,27 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
         }
 }
 
-// 2 x 8 block as two 2 x 4 halves: halves the live temporaries (needed to fit 3 CTAs of 256 threads per SM)
+// The 2 x 16 accumulator block of one thread (tile.cuh: rows gi[0..1], columns cbase + 8 (cc/2) + 2 t + cc%2) as four
+// 2 x 4 quarters in a rolled loop: one copy of the evaluation code, few live temporaries.
 template <bool SAME>
-__device__ __forceinline__ void eval_block_2x8(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
+__device__ __forceinline__ void eval_block_acc(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
                                                int lda, int na, const int (&gi)[2], const double *__restrict__ Xb,
-                                               int ldb, int nb, const int (&gj)[8], double diag_add,
-                                               double (&out)[2][8]) {
+                                               int ldb, int nb, int cbase, int t, double diag_add,
+                                               double (&out)[2][16]) {
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {  // rolled: one copy of the evaluation code
+    for (int h = 0; h < 4; ++h) {
         int gjh[4];
         double o[2][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gjh[c] = h ? gj[4 + c] : gj[c];
+        for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
         eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int hh = 0; hh < 4; ++hh)
+            if (hh == h) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (h) out[r][4 + c] = o[r][c];
-                else out[r][c] = o[r][c];
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) out[r][4 * hh + c] = o[r][c];
             }
     }
 }

@@ -22,45 +22,42 @@ namespace gpl {
 namespace {
 
 #ifndef GPL_LML_CTAS_PER_SM
-#define GPL_LML_CTAS_PER_SM 2
+#define GPL_LML_CTAS_PER_SM 4
 #endif
-#ifndef GPL_LML_KC
-#define GPL_LML_KC 32  // columns per pipeline stage (two stages of row + column operand = KC * 2 KiB)
-#endif
-constexpr int LKC = GPL_LML_KC;
-constexpr int LCH = LKC * TS;  // doubles per operand stage
-static_assert(4 * LCH <= 2 * TILE_ELEMS, "stages must fit the staging buffer");
+constexpr int LKC = 16;        // columns per pipeline stage
+constexpr int LCH = LKC * TS;  // doubles per operand stage: two stages x (row + column operand) = the 32 KiB buffer S
+static_assert(4 * LCH == TILE_ELEMS, "two stages of both operands fill the staging buffer exactly");
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
-// Shared memory of one CTA.  The staging buffer S holds, in turn: the two LKC-column pipeline stages of the row
-// operand (S[0], S[LCH]) and of the column operand (S[2 LCH], S[3 LCH]) during the update loop; the
-// factorisation scratch of the diagonal tile; the staged T tile of the triangular solve; one whole tile for the
-// single-buffered alpha / gradient phases.  Only the gradient kernel carries a second whole-tile buffer (Bt),
-// so the plain log-likelihood kernel fits three CTAs per SM (72 KiB each) and the gradient kernel two.
+// Shared memory of one CTA (~48 KiB: four CTAs per SM).  The 32 KiB buffer S holds, in turn: the two 16-column
+// pipeline stages of the row operand (S[0], S[LCH]) and of the column operand (S[2 LCH], S[3 LCH]) during the
+// update loop; the factorisation scratch of the diagonal tile; the factor L_jj of the diagonal tile, re-loaded
+// from the workspace (L2) for the triangular solve of every tile below it; one whole tile for the single-buffered
+// alpha / gradient phases.  Only the gradient kernel carries a second whole-tile buffer (Bt).
 template <bool GRAD>
 struct __align__(16) LmlSmem {
-    double S[4 * LCH > TILE_ELEMS ? 4 * LCH : TILE_ELEMS];
-    double W[TILE_ELEMS];  // inverse of the current diagonal tile
+    double S[TILE_ELEMS];
     double Bt[GRAD ? TILE_ELEMS : 2];
+    double D[DSIZE];  // inverses of the four 16 x 16 diagonal blocks of the current diagonal tile
     ItemScalars sc;
-    double rsbuf[32];
+    double rsbuf[16];
     double pivbuf[TS];
     double ybuf[TS];
+    double tmp16[16];
     double L16s[256];
-    double W16s[256];
     double gsum[GPL_MAX_THETA];
-    double red[8];
+    double red[NWARPS];
     double logdet;
     int item;
     int info;
 };
 
-__device__ __forceinline__ void block_indices(const TMap &tm, int i, int j, int (&gi)[2], int (&gj)[8]) {
+__device__ __forceinline__ void block_indices(const TMap &tm, int i, int j, int (&gi)[2], int (&gj)[NCC]) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) gj[cc] = j * TS + col_of(tm, cc);
+    for (int cc = 0; cc < NCC; ++cc) gj[cc] = j * TS + col_of(tm, cc);
 }
 
 }  // namespace
@@ -105,19 +102,20 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                 const int Q = (TS / LKC) * j;  // pipeline steps: LKC columns of L_ik / L_jk each, k = 0..j-1
                 const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1) are contiguous
                 const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;
-                // all readers of the staging buffer (previous tile) are done: start the first loads, then
-                // generate the covariance tile while they are in flight
+                // all readers of S (previous tile) are done: start the first loads, then generate the covariance
+                // tile while they are in flight
                 __syncthreads();
                 if (Q > 0) {
                     block_load_async<LCH * 8>(sm.S, srcA, tid);
                     if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH, srcB, tid);
                     cp_async_commit();
                 }
-                double acc[2][8];
+                double acc[2][NCC];
                 {
-                    int gi[2], gj[8];
-                    block_indices(tm, i, j, gi, gj);
-                    eval_block_2x8<true>(P, sm.sc, X, n, n, gi, X, n, n, gj, diag_add, acc);
+                    int gi[2];
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
+                    eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc);
                 }
                 double ytmp = 0.0;
                 if (diag && tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
@@ -137,31 +135,43 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                     if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * LKC, tid, 0, LKC);
                 }
                 if (diag) {
-                    __syncthreads();  // the staging buffers become the factorisation scratch
-                    double w[2][8];
-                    const int fail = tile_potrf_inv(acc, w, tm, sm.S, sm.L16s, sm.W16s, sm.rsbuf, sm.pivbuf, tid);
+                    __syncthreads();  // S becomes the factorisation scratch
+                    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
                     if (tid == 0 && fail >= 0 && sm.info == 0) sm.info = j * TS + fail + 1;
                     acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
-                    acc_to_tile(sm.W, w, tm);
+                    __syncthreads();  // scratch no longer read
+                    acc_to_tile(sm.S, acc, tm);  // L_jj stays in S for the forward solve (and, for column 0, the solves below)
                     if (tid < TS) sm.ybuf[tid] = ytmp;
-                    __syncthreads();
-                    if (tid < TS) wsZ[j * TS + tid] = tile_row_dot(sm.W, sm.ybuf, tid, 0, tid + 1);  // z_j = W y
+                    tile_forward_solve(sm.S, sm.D, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
+                    if (tid < TS) wsZ[j * TS + tid] = sm.ybuf[tid];
                     if (tid < 32) {
                         double lg = log(sm.pivbuf[tid]) + log(sm.pivbuf[tid + 32]);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
                         if (tid == 0) sm.logdet += lg;
                     }
-                    if (prm.want_grad || prm.keep) tile_store(wsW + (size_t)j * TILE_ELEMS, sm.W, tid);
+                    if (prm.want_grad || prm.keep) {
+                        // full inverse W_jj = L_jj^-1 for the alpha / gradient / prediction phases: X L' = I gives W'
+                        double e[2][NCC];
+#pragma unroll
+                        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                            for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+                        tile_trsm_ld(e, sm.S, sm.D, tm);
+                        acc_to_tile_t(wsW + (size_t)j * TILE_ELEMS, e, tm);
+                    }
                 } else {
-                    // L_ij = T_ij W_jj'  (W lower triangular: k < c0 + 32 for this warp's columns)
-                    __syncthreads();
-                    acc_to_tile(sm.S, acc, tm);
-                    __syncthreads();
-                    double x[2][8];
-                    acc_zero(x);
-                    tile_mma<false>(x, sm.S, sm.W, tm, 0, tm.c0 + 32);
-                    acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, x, tm);
+                    // L_ij = T_ij L_jj^-T: row operand from the accumulator registers; L_jj re-loaded into S (it is
+                    // still there for column 0, whose tiles have no update loop); its block inverses are still in D
+                    if (Q > 0) {
+                        __syncthreads();
+                        tile_load_async(sm.S, wsL + tri_index(j, j) * TILE_ELEMS, tid);
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                        __syncthreads();
+                    }
+                    tile_trsm_ld(acc, sm.S, sm.D, tm);
+                    acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
                 }
             }
         }
@@ -217,7 +227,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
         // M, so that M_kj can be the column operand of C += A B' (B'(k, n) = M_kj(k, n)).
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
-                double acc[2][8];
+                double acc[2][NCC];
                 if (i == j) {
                     __syncthreads();
                     tile_load_async(sm.S, wsW + (size_t)j * TILE_ELEMS, tid);
@@ -245,7 +255,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                 acc_to_tile_t(sm.Bt, acc, tm);
                 cp_async_wait<0>();
                 __syncthreads();
-                double mij[2][8];
+                double mij[2][NCC];
                 acc_zero(mij);
                 tile_mma<true>(mij, sm.S, sm.Bt, tm, 0, TS);
                 acc_to_tile_t(wsM + tri_index(i, j) * TILE_ELEMS, mij, tm);
@@ -257,7 +267,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
         // dlml/dtheta_s = -1/2 sum_ij (P - alpha alpha')_ij dK_ij/dtheta_s.
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
-                double acc[2][8];
+                double acc[2][NCC];
                 acc_zero(acc);
                 for (int k = i; k < nt; ++k) {
                     __syncthreads();
@@ -268,14 +278,14 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                     __syncthreads();
                     tile_mma<false>(acc, sm.S, (i == j) ? sm.S : sm.Bt, tm, 0, TS);
                 }
-                int gi[2], gj[8];
+                int gi[2], gj[NCC];
                 block_indices(tm, i, j, gi, gj);
                 const double sym = (i == j) ? 1.0 : 2.0;
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) acc[mb][cc] = sym * (acc[mb][cc] - wsAl[gi[mb]] * wsAl[gj[cc]]);
-                contract_grad_block<2, 8>(P, sm.sc, X, n, n, gi, gj, acc, sm.gsum);
+                    for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = sym * (acc[mb][cc] - wsAl[gi[mb]] * wsAl[gj[cc]]);
+                contract_grad_block<2, NCC>(P, sm.sc, X, n, n, gi, gj, acc, sm.gsum);
             }
         }
         __syncthreads();
@@ -287,7 +297,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
 __global__ void __launch_bounds__(NTHREADS, GPL_LML_CTAS_PER_SM) lml_batched_kernel(const __grid_constant__ LmlParams prm) {
     lml_batched_body<false>(prm);
 }
-__global__ void __launch_bounds__(NTHREADS, 2) lml_batched_grad_kernel(const __grid_constant__ LmlParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 3) lml_batched_grad_kernel(const __grid_constant__ LmlParams prm) {
     lml_batched_body<true>(prm);
 }
 

@@ -37,23 +37,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
 
     const int nslab = (m + TS - 1) / TS;
     for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
-        int gj[8];
+        int gj[NCC];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) gj[cc] = s * TS + col_of(tm, cc);
-        double csq[8], cmean[8];
+        for (int cc = 0; cc < NCC; ++cc) gj[cc] = s * TS + col_of(tm, cc);
+        double csq[NCC], cmean[NCC];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) csq[cc] = cmean[cc] = 0.0;
+        for (int cc = 0; cc < NCC; ++cc) csq[cc] = cmean[cc] = 0.0;
         for (int i = 0; i < nt; ++i) {
             int gi[2];
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
-            double acc[2][8];
-            eval_block_2x8<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, gj, 0.0, acc);
+            double acc[2][NCC];
+            eval_block_acc<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, s * TS, tm.t, 0.0, acc);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
                 const double al = gi[mb] < n ? prm.alpha[gi[mb]] : 0.0;
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) cmean[cc] = fma(acc[mb][cc], al, cmean[cc]);
+                for (int cc = 0; cc < NCC; ++cc) cmean[cc] = fma(acc[mb][cc], al, cmean[cc]);
             }
             if (!prm.want_var) continue;
             // acc -= sum_{k<i} L_ik V_k : row operand L_ik, column operand V_k' (stored transposed)
@@ -73,20 +73,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
             acc_to_tile_t(sm.Bt, acc, tm);
             cp_async_wait<0>();
             __syncthreads();
-            double v[2][8];
-            acc_zero(v);
-            tile_mma<false>(v, sm.A, sm.Bt, tm, 0, tm.r0 + 16);
+            acc_zero(acc);
+            tile_mma<false>(acc, sm.A, sm.Bt, tm, 0, tm.r0 + 16);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) csq[cc] = fma(v[mb][cc], v[mb][cc], csq[cc]);
-            if (i + 1 < nt) acc_to_tile_t(wsV + (size_t)i * TILE_ELEMS, v, tm);
+                for (int cc = 0; cc < NCC; ++cc) csq[cc] = fma(acc[mb][cc], acc[mb][cc], csq[cc]);
+            if (i + 1 < nt) acc_to_tile_t(wsV + (size_t)i * TILE_ELEMS, acc, tm);
         }
-        // reduce the per-thread partials: 32 partials per column (4 row bands x 8 lanes g), fixed order
-        const int slot = (tid >> 6) * 8 + tm.g;
+        // reduce the per-thread partials: 32 partials per column (4 warps x 8 lane groups g), fixed order
+        const int slot = (tid >> 5) * 8 + tm.g;
         __syncthreads();
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) sm.part[slot * TS + col_of(tm, cc)] = cmean[cc];
+        for (int cc = 0; cc < NCC; ++cc) sm.part[slot * TS + col_of(tm, cc)] = cmean[cc];
         __syncthreads();
         if (tid < TS && s * TS + tid < m) {
             double sum = 0.0;
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
         if (prm.want_var) {
             __syncthreads();
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) sm.part[slot * TS + col_of(tm, cc)] = csq[cc];
+            for (int cc = 0; cc < NCC; ++cc) sm.part[slot * TS + col_of(tm, cc)] = csq[cc];
             __syncthreads();
             if (tid < TS && s * TS + tid < m) {
                 double sum = 0.0;
@@ -114,13 +113,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
     }
 }
 
-// out (n x S) = L Z : grid = nt CTAs (tile row i), thread (row = tid % 64, sample lane = tid / 64)
+// out (n x S) = L Z : grid = nt CTAs (tile row i), thread (row = tid % 64, sample lane = tid / 64: 2 samples at a time)
 __global__ void __launch_bounds__(NTHREADS) sample_kernel(const double *tiles, int nt, int n, const double *Z, int S,
                                                           double *out) {
     __shared__ __align__(16) double T[TILE_ELEMS];
     const int tid = threadIdx.x, i = blockIdx.x;
     const int row = tid & (TS - 1), sl = tid >> 6;
-    for (int s0 = 0; s0 < S; s0 += 4) {
+    for (int s0 = 0; s0 < S; s0 += NTHREADS / TS) {
         const int s = s0 + sl;
         double acc = 0.0;
         for (int k = 0; k <= i; ++k) {

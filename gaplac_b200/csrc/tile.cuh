@@ -1,9 +1,14 @@
 // 64 x 64 FP64 tile primitives shared by the batched factorisation, the posterior/predict kernels and the
-// large-n path.  One CTA of 256 threads (8 warps) owns one tile; the contraction runs on the FP64 tensor-core
-// path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4): on sm_100a DMMA has the same peak as vector DFMA (37 TFLOP/s
+// large-n path.  One CTA of 128 threads (4 warps) owns one tile; the contraction runs on the FP64 tensor-core
+// path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  On sm_100a DMMA has the same peak as vector DFMA (37 TFLOP/s
 // measured, tools/fp64_peak.cu) but its fragments are loaded from shared memory without the redundant
-// broadcast reads a register-tiled DFMA loop needs, which is what bounded the first versions of these kernels
-// (profiles/ncu_lml_r01_v1_*: shared-memory wavefronts at 62 % of peak, FP64 pipe at 41 %).
+// broadcast reads a register-tiled DFMA loop needs (profiles/README.md, v1 -> v2).
+//
+// Why 4 warps with 16 x 64 warp tiles: (a) a CTA needs only 128 x <=128 registers and ~40 KiB of shared memory,
+// so four independent GPs are resident per SM and the latency-bound stretches of one (pivot chains, barriers,
+// first loads) are covered by the tensor work of the others; (b) every warp owns complete rows of the tile, so
+// the triangular solve L_ij = T_ij L_jj^-T takes its row operand straight from the accumulator registers
+// (quad shuffles), with no staging of T through shared memory.
 //
 // Tile storage (global workspace and shared memory alike): 64 x 64 doubles = 32 KiB, dense, column-major with
 // an XOR swizzle of the row index:  element (r, c) lives at  c*64 + (r ^ ((c & 3) << 2)).
@@ -13,9 +18,9 @@
 // 8-byte banks per half-warp: conflict-free LDS.64, 2 wavefronts per 256 bytes.
 //
 // GEMM form used everywhere:  C (+|-)= A * B'  with A = (rows x k) and B = (cols x k), both in tile format.
-// Thread -> accumulator map (warp w: wr = w/2 -> 16 rows, wc = w%2 -> 32 columns; lane: g = lane/4, t = lane%4):
-//   rows  row_of(mb)  = wr*16 + 8*mb + g,               mb = 0, 1
-//   cols  col_of(cc)  = wc*32 + 8*(cc/2) + 2*t + cc%2,  cc = 0..7       -> acc[2][8]
+// Thread -> accumulator map (warp w -> rows 16w..16w+15; lane: g = lane/4, t = lane%4):
+//   rows  row_of(mb)  = 16*w + 8*mb + g,            mb = 0, 1
+//   cols  col_of(cc)  = 8*(cc/2) + 2*t + cc%2,      cc = 0..15      -> acc[2][16]
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,7 +30,9 @@ namespace gpl {
 constexpr int TS = 64;                 // tile edge
 constexpr int TILE_ELEMS = TS * TS;    // 4096 doubles
 constexpr int TILE_BYTES = TILE_ELEMS * 8;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 128;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int NCC = 16;                // accumulator columns per thread
 
 __host__ __device__ __forceinline__ long long tri_index(int i, int j) { return (long long)i * (i + 1) / 2 + j; }
 
@@ -34,21 +41,19 @@ __host__ __device__ __forceinline__ int tidx(int r, int c) { return c * TS + (r 
 
 struct TMap {
     int r0;  // first row of the warp's 16-row band
-    int c0;  // first column of the warp's 32-column band
     int g;   // lane / 4
     int t;   // lane % 4
 };
 __device__ __forceinline__ TMap thread_map(int tid) {
-    const int w = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     TMap m;
-    m.r0 = (w >> 1) * 16;
-    m.c0 = (w & 1) * 32;
+    m.r0 = (tid >> 5) * 16;
     m.g = lane >> 2;
     m.t = lane & 3;
     return m;
 }
 __device__ __forceinline__ int row_of(const TMap &tm, int mb) { return tm.r0 + 8 * mb + tm.g; }
-__device__ __forceinline__ int col_of(const TMap &tm, int cc) { return tm.c0 + 8 * (cc >> 1) + 2 * tm.t + (cc & 1); }
+__device__ __forceinline__ int col_of(const TMap &tm, int cc) { return 8 * (cc >> 1) + 2 * tm.t + (cc & 1); }
 
 // ---- global <-> shared movement -------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -74,15 +79,6 @@ __device__ __forceinline__ void block_load_async(double *smem, const double *__r
 __device__ __forceinline__ void tile_load_async(double *smem, const double *__restrict__ gmem, int tid) {
     block_load_async<TILE_BYTES>(smem, gmem, tid);
 }
-__device__ __forceinline__ void half_tile_load_async(double *smem, const double *__restrict__ gmem, int tid) {
-    block_load_async<TILE_BYTES / 2>(smem, gmem, tid);
-}
-// 16 whole columns of a tile (8 KiB): the pipeline stage of the factorisation kernels
-constexpr int KC = 16;
-constexpr int CHUNK_ELEMS = KC * TS;
-__device__ __forceinline__ void chunk_load_async(double *smem, const double *__restrict__ gmem, int tid) {
-    block_load_async<CHUNK_ELEMS * 8>(smem, gmem, tid);
-}
 
 __device__ __forceinline__ void tile_store(double *__restrict__ gmem, const double *smem, int tid) {
 #pragma unroll
@@ -93,37 +89,31 @@ __device__ __forceinline__ void tile_store(double *__restrict__ gmem, const doub
 }
 
 // ---- register block <-> tile (shared or global) ------------------------------------------------------------
-__device__ __forceinline__ void acc_zero(double (&acc)[2][8]) {
+__device__ __forceinline__ void acc_zero(double (&acc)[2][NCC]) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) acc[mb][cc] = 0.0;
+        for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = 0.0;
 }
 // tile element (row, col) <- acc
-__device__ __forceinline__ void acc_to_tile(double *T, const double (&acc)[2][8], const TMap &tm) {
+__device__ __forceinline__ void acc_to_tile(double *T, const double (&acc)[2][NCC], const TMap &tm) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) T[tidx(row_of(tm, mb), col_of(tm, cc))] = acc[mb][cc];
+        for (int cc = 0; cc < NCC; ++cc) T[tidx(row_of(tm, mb), col_of(tm, cc))] = acc[mb][cc];
 }
 // transposed: tile element (col, row) <- acc
-__device__ __forceinline__ void acc_to_tile_t(double *T, const double (&acc)[2][8], const TMap &tm) {
+__device__ __forceinline__ void acc_to_tile_t(double *T, const double (&acc)[2][NCC], const TMap &tm) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) T[tidx(col_of(tm, cc), row_of(tm, mb))] = acc[mb][cc];
+        for (int cc = 0; cc < NCC; ++cc) T[tidx(col_of(tm, cc), row_of(tm, mb))] = acc[mb][cc];
 }
-__device__ __forceinline__ void acc_from_tile(double (&acc)[2][8], const double *T, const TMap &tm) {
+__device__ __forceinline__ void acc_from_tile(double (&acc)[2][NCC], const double *T, const TMap &tm) {
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) acc[mb][cc] = T[tidx(row_of(tm, mb), col_of(tm, cc))];
-}
-__device__ __forceinline__ void acc_from_tile_t(double (&acc)[2][8], const double *T, const TMap &tm) {
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) acc[mb][cc] = T[tidx(col_of(tm, cc), row_of(tm, mb))];
+        for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = T[tidx(row_of(tm, mb), col_of(tm, cc))];
 }
 
 // ---- GEMM core on the FP64 tensor-core path ------------------------------------------------------------------
@@ -134,98 +124,140 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // acc (+|-)= A[rows, k0:k1] * B[cols, k0:k1]'   for the n-blocks nb with (NBMASK >> nb) & 1 (8 columns each).
-// k0, k1 multiples of 4.  A and B are tiles (or leading column ranges of tiles) in tile format.
-template <bool SUB, int NBMASK = 0xF>
-__device__ __forceinline__ void tile_mma(double (&acc)[2][8], const double *__restrict__ A,
+// k0, k1 multiples of 4.  A and B are tiles (or runs of whole columns starting at a multiple of 4) in tile format.
+template <bool SUB, int NBMASK = 0xFF>
+__device__ __forceinline__ void tile_mma(double (&acc)[2][NCC], const double *__restrict__ A,
                                          const double *__restrict__ B, const TMap &tm, int k0, int k1) {
-    // (k + t) & 3 == t for k % 4 == 0: the swizzle is a per-lane constant
+    // (k + t) & 3 == t for k % 4 == 0: the swizzle is a per-lane constant.  For the column operand the row index is
+    // 8 nb + g: xor with sw = 4t flips bit 2 of g and (for t >= 2) bit 3, i.e. swaps odd and even n-blocks.
     const int sw = tm.t << 2;
     const double *pa0 = A + tm.t * TS + ((tm.r0 + tm.g) ^ sw);
     const double *pa1 = A + tm.t * TS + ((tm.r0 + 8 + tm.g) ^ sw);
-    const double *pb = B + tm.t * TS;
-    const int bo0 = (tm.c0 + tm.g) ^ sw, bo1 = (tm.c0 + 8 + tm.g) ^ sw, bo2 = (tm.c0 + 16 + tm.g) ^ sw,
-              bo3 = (tm.c0 + 24 + tm.g) ^ sw;
-#pragma unroll 4
+    const double *pbe = B + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);        // even n-blocks
+    const double *pbo = B + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));  // odd n-blocks
+#pragma unroll 2
     for (int k = k0; k < k1; k += 4) {
         double a0 = pa0[k * TS], a1 = pa1[k * TS];
         if (SUB) {
             a0 = -a0;
             a1 = -a1;
         }
-        if (NBMASK & 1) {
-            const double b = pb[k * TS + bo0];
-            dmma884(acc[0][0], acc[0][1], a0, b);
-            dmma884(acc[1][0], acc[1][1], a1, b);
-        }
-        if (NBMASK & 2) {
-            const double b = pb[k * TS + bo1];
-            dmma884(acc[0][2], acc[0][3], a0, b);
-            dmma884(acc[1][2], acc[1][3], a1, b);
-        }
-        if (NBMASK & 4) {
-            const double b = pb[k * TS + bo2];
-            dmma884(acc[0][4], acc[0][5], a0, b);
-            dmma884(acc[1][4], acc[1][5], a1, b);
-        }
-        if (NBMASK & 8) {
-            const double b = pb[k * TS + bo3];
-            dmma884(acc[0][6], acc[0][7], a0, b);
-            dmma884(acc[1][6], acc[1][7], a1, b);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            if ((NBMASK >> nb) & 1) {
+                const double b = ((nb & 1) ? pbo : pbe)[k * TS + 16 * (nb >> 1)];
+                dmma884(acc[0][2 * nb], acc[0][2 * nb + 1], a0, b);
+                dmma884(acc[1][2 * nb], acc[1][2 * nb + 1], a1, b);
+            }
         }
     }
 }
 
-// ---- Cholesky of the diagonal tile with its inverse, blocked ---------------------------------------------------
-// In: acc = the 64 x 64 SPD tile (lower part used).  Out: acc = L (zeros above the diagonal), w = L^-1.
-// The tile is processed in four 16-column panels (a rolled loop: the whole routine is ~20 KiB of SASS; the first,
-// fully unrolled version was 270 KiB and made instruction fetch the second largest stall of the kernel):
-//   1. the owners of the panel's columns (acc) and of the panel's rows of the running inverse (w) publish them;
-//   2. warp 0 factors the 16 x 16 diagonal block in registers (one row per lane, pivots and columns exchanged
-//      with warp shuffles: no block barrier inside) and inverts it by forward substitution;
-//   3. all threads form the panel of L below the block (P * W16') and the new rows of the inverse (W16 * R);
-//   4. all warps apply the rank-16 update to their register blocks of the trailing tile and of the inverse (DMMA).
-// Three block barriers per panel.  The inverse rides along as a block Gauss-Jordan on the identity, so the
-// triangular solves of the tiles below (L_ij = T_ij L_jj^-T) become plain GEMMs.
-// scratch: 4096 doubles (P, R, Lp, Rp, each 64 x 16 in tile format; the three barriers order every reuse);
-// L16s / W16s: 256 doubles each; rsbuf: 16 + 16 (reciprocal pivots, pivot-column exchange); pivbuf: 64 (pivots).
-// Returns (in warp 0) -1 or the local index of the first non-positive pivot.
-__device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2][8], const TMap &tm, double *scratch,
-                                           double *L16s, double *W16s, double *rsbuf, double *pivbuf, int tid) {
-    const int warp = tid >> 5, lane = tid & 31, wr = warp >> 1, wc = warp & 1;
-    double *P = scratch;         // columns of the panel:           element (row, k) at tidx(row, k)
-    double *R = P + 1024;        // rows of the inverse, as (col, k): tidx(col, k)
-    double *Lp = P + 2048;       // panel of L, (row, k)
-    double *Rp = P + 3072;       // new rows of the inverse, (col, k)
-    double *colx = rsbuf + 16;   // pivot-column exchange of warp 0
+// ---- triangular solve from the accumulator registers -------------------------------------------------------------
+// acc := acc * W'   for a lower-triangular W (64 x 64, tile format, in shared memory):
+//   X[:, n] = sum_{k <= n} T[:, k] W[n, k].
+// The row operand T is the accumulator itself: the A fragment of k-chunk kap (columns 4 kap .. 4 kap + 3) for lane
+// (g, t) is T[row][4 kap + t], which lives in lane (g, 2 (kap & 1) + t / 2), register 2 (kap / 2) + (t & 1): two
+// quad shuffles and a select.  Output n-blocks are produced in two groups, high half first, so the result can
+// overwrite the accumulator in place (X[:, n-block] never needs T columns beyond its own block).
+template <int NB_LO, int NB_HI>
+__device__ __forceinline__ void trsm_group(double (&acc)[2][NCC], const double *__restrict__ W, const TMap &tm) {
+    constexpr int NG = NB_HI - NB_LO;
+    double x[2][2 * NG];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) w[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+        for (int q = 0; q < 2 * NG; ++q) x[mb][q] = 0.0;
+    const int sw = tm.t << 2;
+    const int lane_base = tm.g << 2;
+    const double *pbe = W + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);
+    const double *pbo = W + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));
+#pragma unroll
+    for (int kap = 0; kap < 2 * NB_HI; ++kap) {
+        const int nbs = kap >> 1, h = kap & 1;
+        const int src = lane_base | (2 * h + (tm.t >> 1));
+        double a[2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            const double v0 = __shfl_sync(0xffffffffu, acc[mb][2 * nbs], src);
+            const double v1 = __shfl_sync(0xffffffffu, acc[mb][2 * nbs + 1], src);
+            a[mb] = (tm.t & 1) ? v1 : v0;
+        }
+#pragma unroll
+        for (int nb = (nbs > NB_LO ? nbs : NB_LO); nb < NB_HI; ++nb) {
+            const double b = ((nb & 1) ? pbo : pbe)[4 * kap * TS + 16 * (nb >> 1)];
+            dmma884(x[0][2 * (nb - NB_LO)], x[0][2 * (nb - NB_LO) + 1], a[0], b);
+            dmma884(x[1][2 * (nb - NB_LO)], x[1][2 * (nb - NB_LO) + 1], a[1], b);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int q = 0; q < 2 * NG; ++q) acc[mb][2 * NB_LO + q] = x[mb][q];
+}
+// acc := acc * W' for a full lower-triangular inverse tile W (used where the inverse exists anyway: large-n path)
+__device__ __forceinline__ void tile_trsm_w(double (&acc)[2][NCC], const double *__restrict__ W, const TMap &tm) {
+    trsm_group<4, 8>(acc, W, tm);
+    trsm_group<0, 4>(acc, W, tm);
+}
+
+// ---- Cholesky of the diagonal tile, blocked -----------------------------------------------------------------------
+// In: acc = the 64 x 64 SPD tile (lower part used).  Out: acc = L (zeros above the diagonal) and, in D, the inverses
+// of the four 16 x 16 diagonal blocks of L (block p at D + p*DBLK, element (i, k) at i*DLD + k; DLD = 20 makes the
+// DMMA fragment loads of these blocks bank-conflict free).  The tile is processed in four 16-column panels (a rolled
+// loop keeps the routine small in the instruction cache):
+//   1. every warp publishes its 16 rows of the panel's columns;
+//   2. warp 0 factors the 16 x 16 diagonal block in registers (one row per lane, pivots and columns exchanged
+//      with warp shuffles: no block barrier inside) and inverts it by forward substitution;
+//   3. all threads form the panel of L below the block (P * W16');
+//   4. all warps apply the rank-16 update to their register blocks of the trailing tile (DMMA).
+// Three block barriers per panel.  The triangular solves that follow (tile_trsm_ld, tile_forward_solve) use L and the
+// four block inverses, so the full 64 x 64 inverse is only formed where a caller needs it (tile_inverse_from_ld).
+// scratch: 2048 doubles (P, Lp: 64 x 16 in tile format); L16s: 256; rsbuf: 16; pivbuf: 64 (pivots, for logdet).
+// Returns (in warp 0) -1 or the local index of the first non-positive pivot.
+constexpr int DLD = 20;
+constexpr int DBLK = 16 * DLD;    // 320 doubles per block inverse
+constexpr int DSIZE = 4 * DBLK;   // 1280 doubles = 10 KiB per diagonal tile
+
+template <int PC>
+__device__ __forceinline__ void potrf_panel_update(double (&acc)[2][NCC], const TMap &tm, int p, int warp,
+                                                   const double *Lp) {
+    constexpr int MASK = 0x3 << (2 * PC);
+    if (PC == p) {  // finished columns of L
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mb][4 * PC + q] = Lp[tidx(row_of(tm, mb), col_of(tm, q))];
+    } else if (PC > p && warp >= PC) {  // trailing lower part: T -= Lp Lp'
+        tile_mma<true, MASK>(acc, Lp, Lp, tm, 0, 16);
+    }
+}
+
+__device__ __forceinline__ int tile_potrf(double (&acc)[2][NCC], const TMap &tm, double *scratch, double *L16s,
+                                          double *D, double *rsbuf, double *pivbuf, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    double *P = scratch;         // columns of the panel: element (row, k) at tidx(row, k)
+    double *Lp = scratch + 1024; // panel of L, (row, k)
     int fail = -1;
 #pragma unroll 1
     for (int p = 0; p < 4; ++p) {
-        const int hs = p & 1;  // which column half of the owning warps holds the panel
-        // 1. publish
-        if (wc == (p >> 1)) {
+        double *W16s = D + p * DBLK;
+        // 1. publish: the panel's columns are accumulator columns 4p..4p+3 of every thread
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
+        for (int pp = 0; pp < 4; ++pp)
+            if (pp == p) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    P[tidx(row_of(tm, mb), col_of(tm, q) - tm.c0)] = hs ? acc[mb][4 + q] : acc[mb][q];  // panel-local column
-        }
-        if (wr == p) {
+                for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) R[tidx(col_of(tm, cc), 8 * mb + tm.g)] = w[mb][cc];
-        }
+                    for (int q = 0; q < 4; ++q) P[tidx(row_of(tm, mb), col_of(tm, q))] = acc[mb][4 * pp + q];
+            }
         __syncthreads();
         // 2. warp 0: 16 x 16 Cholesky, one row per lane, pivots and columns exchanged with warp shuffles
         if (warp == 0) {
-            const int c_own = lane & 15;  // row owned by this lane (lanes 16..31 mirror 0..15)
+            const int r_own = lane & 15;  // row owned by this lane (lanes 16..31 mirror 0..15)
             double a[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) a[c] = P[tidx(16 * p + c_own, c)];
+            for (int c = 0; c < 16; ++c) a[c] = P[tidx(16 * p + r_own, c)];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 double piv = __shfl_sync(0xffffffffu, a[c], c);
@@ -239,7 +271,7 @@ __device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2
                     rsbuf[c] = rs;
                 }
                 const double l = a[c] * rs;
-                a[c] = (c_own >= c) ? l : 0.0;
+                a[c] = (r_own >= c) ? l : 0.0;
 #pragma unroll
                 for (int c2 = c + 1; c2 < 16; ++c2) {
                     const double l2 = __shfl_sync(0xffffffffu, l, c2);
@@ -248,12 +280,12 @@ __device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2
             }
             if (lane < 16) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) L16s[c * 16 + c_own] = a[c];  // L16[r][c], column-major
+                for (int c = 0; c < 16; ++c) L16s[c * 16 + r_own] = a[c];  // L16[r][c], column-major
             }
             __syncwarp();
-            double x[16];  // column c_own of L16^-1 (axpy-form forward substitution)
+            double x[16];  // column r_own of L16^-1 (axpy-form forward substitution)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = (i == c_own) ? 1.0 : 0.0;
+            for (int i = 0; i < 16; ++i) x[i] = (i == r_own) ? 1.0 : 0.0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 x[c] *= rsbuf[c];
@@ -262,82 +294,134 @@ __device__ __forceinline__ int tile_potrf_inv(double (&acc)[2][8], double (&w)[2
             }
             if (lane < 16) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) W16s[i * 16 + c_own] = x[i];  // W16[i][c], row-major
+                for (int i = 0; i < 16; ++i) W16s[i * DLD + r_own] = x[i];  // W16[i][c]
             }
         }
         __syncthreads();
-        // 3a. Lp: rows below the block = P * W16', rows of the block = L16, rows above = 0
+        // 3. Lp (thread = one row, 8 of the 16 panel columns): rows below the block = P * W16', rows of the block =
+        //    L16, rows above = 0
         {
-            const int row = tid & 63, cg = tid >> 6;
-            double out[4] = {0.0, 0.0, 0.0, 0.0};
+            const int row = tid & 63, c8 = (tid >> 6) * 8;
+            double out[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) out[q] = 0.0;
             if (row >= 16 * (p + 1)) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const double pk = P[tidx(row, k)];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = 4 * cg + q;
-                        if (k <= c) out[q] = fma(pk, W16s[c * 16 + k], out[q]);
+                    for (int q = 0; q < 8; ++q) {
+                        if (k <= c8 + q) out[q] = fma(pk, W16s[(c8 + q) * DLD + k], out[q]);
                     }
                 }
             } else if (row >= 16 * p) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) out[q] = L16s[(4 * cg + q) * 16 + (row - 16 * p)];
+                for (int q = 0; q < 8; ++q) out[q] = L16s[(c8 + q) * 16 + (row - 16 * p)];
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) Lp[tidx(row, 4 * cg + q)] = out[q];
-        }
-        // 3b. Rp = W16 * R   (element (col, k) <- sum_{k2 <= k} W16[k][k2] R(col, k2))
-        {
-            const int col = tid & 63, kg = tid >> 6;
-            double out[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
-                const double rv = R[tidx(col, k2)];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = 4 * kg + q;
-                    if (k2 <= k) out[q] = fma(W16s[k * 16 + k2], rv, out[q]);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Rp[tidx(col, 4 * kg + q)] = out[q];
+            for (int q = 0; q < 8; ++q) Lp[tidx(row, c8 + q)] = out[q];
         }
         __syncthreads();
-        // 4. register-block updates.  Column half h (n-blocks 2h, 2h+1) of this warp belongs to panel pc = 2 wc + h.
+        // 4. register-block updates, per 16-column panel PC of the accumulator (n-blocks 2 PC, 2 PC + 1)
+        potrf_panel_update<0>(acc, tm, p, warp, Lp);
+        potrf_panel_update<1>(acc, tm, p, warp, Lp);
+        potrf_panel_update<2>(acc, tm, p, warp, Lp);
+        potrf_panel_update<3>(acc, tm, p, warp, Lp);
+    }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int pc = 2 * wc + h;
-            if (pc == p) {  // finished columns of L
+    for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb)
+        for (int cc = 0; cc < NCC; ++cc)
+            if (col_of(tm, cc) > row_of(tm, mb)) acc[mb][cc] = 0.0;
+    return fail;
+}
+
+// ---- triangular solve with L and its block inverses, from the accumulator registers ------------------------------------
+// acc := acc * L^-T  (X L' = T), L = 64 x 64 lower-triangular tile in shared memory (tile format), D = its four block
+// inverses.  Blocked forward substitution over the four 16-column panels, everything in place:
+//   X_p = (T_p - sum_{q<p} X_q L_pq') W16_p'
+// The row operands (finished panels X_q, and T_p itself) come straight from the accumulator registers: the A fragment
+// of k-chunk kap (columns 4 kap .. 4 kap + 3) for lane (g, t) is acc[row][4 kap + t], which lives in lane
+// (g, 2 (kap & 1) + t / 2), register 2 (kap / 2) + (t & 1): two quad shuffles and a select.
+__device__ __forceinline__ void acc_a_frag(const double (&acc)[2][NCC], int kap_static, const TMap &tm, double (&a)[2]) {
+    const int src = (tm.g << 2) | (2 * (kap_static & 1) + (tm.t >> 1));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        acc[mb][4 * h + q] = Lp[tidx(row_of(tm, mb), col_of(tm, 4 * h + q) - 16 * pc)];
-            } else if (pc > p && wr >= pc) {  // trailing lower part: T -= Lp Lp'
-                if (h == 0) tile_mma<true, 0x3>(acc, Lp, Lp, tm, 0, 16);
-                else tile_mma<true, 0xC>(acc, Lp, Lp, tm, 0, 16);
-            }
-            if (pc <= p) {  // inverse: only columns <= the panel are non-zero in the new rows
-                if (wr > p) {
-                    if (h == 0) tile_mma<true, 0x3>(w, Lp, Rp, tm, 0, 16);
-                    else tile_mma<true, 0xC>(w, Lp, Rp, tm, 0, 16);
-                } else if (wr == p) {
+    for (int mb = 0; mb < 2; ++mb) {
+        const double v0 = __shfl_sync(0xffffffffu, acc[mb][2 * (kap_static >> 1)], src);
+        const double v1 = __shfl_sync(0xffffffffu, acc[mb][2 * (kap_static >> 1) + 1], src);
+        a[mb] = (tm.t & 1) ? v1 : v0;
+    }
+}
+
+template <int P_>
+__device__ __forceinline__ void trsm_ld_panel(double (&acc)[2][NCC], const double *__restrict__ L,
+                                              const double *__restrict__ D, const TMap &tm) {
+    const int sw = tm.t << 2;
+    // column operand rows 16 P_ + 8 nbl + g of L (n-blocks 2 P_, 2 P_ + 1)
+    const double *pl0 = L + tm.t * TS + ((16 * P_ + tm.g) ^ sw);
+    const double *pl1 = L + tm.t * TS + ((16 * P_ + 8 + tm.g) ^ sw);
+    // T_p -= X_q L_pq'  for the finished panels q < P_ (k = columns 16 q .. 16 q + 15)
 #pragma unroll
-                    for (int mb = 0; mb < 2; ++mb)
+    for (int kap = 0; kap < 4 * P_; ++kap) {
+        double a[2];
+        acc_a_frag(acc, kap, tm, a);
+        const double b0 = pl0[4 * kap * TS], b1 = pl1[4 * kap * TS];
+        dmma884(acc[0][4 * P_], acc[0][4 * P_ + 1], -a[0], b0);
+        dmma884(acc[1][4 * P_], acc[1][4 * P_ + 1], -a[1], b0);
+        dmma884(acc[0][4 * P_ + 2], acc[0][4 * P_ + 3], -a[0], b1);
+        dmma884(acc[1][4 * P_ + 2], acc[1][4 * P_ + 3], -a[1], b1);
+    }
+    // X_p = T_p W16_p'   (W16 lower triangular: k-chunk kl feeds n-block nbl >= kl / 2)
+    const double *W16 = D + P_ * DBLK;
+    double x[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            w[mb][4 * h + q] = Rp[tidx(col_of(tm, 4 * h + q), 8 * mb + tm.g)];
-                }
-            }
+    for (int kl = 0; kl < 4; ++kl) {
+        double a[2];
+        acc_a_frag(acc, 4 * P_ + kl, tm, a);
+#pragma unroll
+        for (int nbl = kl >> 1; nbl < 2; ++nbl) {
+            const double b = W16[(8 * nbl + tm.g) * DLD + 4 * kl + tm.t];
+            dmma884(x[0][2 * nbl], x[0][2 * nbl + 1], a[0], b);
+            dmma884(x[1][2 * nbl], x[1][2 * nbl + 1], a[1], b);
         }
     }
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc)
-            if (col_of(tm, cc) > row_of(tm, mb)) acc[mb][cc] = 0.0;
-    return fail;
+        for (int q = 0; q < 4; ++q) acc[mb][4 * P_ + q] = x[mb][q];
+}
+__device__ __forceinline__ void tile_trsm_ld(double (&acc)[2][NCC], const double *__restrict__ L,
+                                             const double *__restrict__ D, const TMap &tm) {
+    trsm_ld_panel<0>(acc, L, D, tm);
+    trsm_ld_panel<1>(acc, L, D, tm);
+    trsm_ld_panel<2>(acc, L, D, tm);
+    trsm_ld_panel<3>(acc, L, D, tm);
+}
+
+// z = L^-1 y for one 64-vector, all threads of the CTA (four block steps, two barriers each):
+//   z_p = W16_p (y_p - sum_{q<p} L_pq z_q).  y is updated in place in `ybuf` (shared); the result replaces it.
+__device__ __forceinline__ void tile_forward_solve(const double *__restrict__ L, const double *__restrict__ D,
+                                                   double *ybuf, double *tmp, int tid) {
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        __syncthreads();
+        if (tid >= 16 * p && tid < 16 * p + 16) {
+            const int il = tid - 16 * p;
+            const double *W16 = D + p * DBLK;
+            double s = 0.0;
+            for (int k = 0; k <= il; ++k) s = fma(W16[il * DLD + k], ybuf[16 * p + k], s);
+            tmp[il] = s;
+        }
+        __syncthreads();
+        if (tid >= 16 * p && tid < 16 * p + 16) ybuf[tid] = tmp[tid - 16 * p];
+        else if (tid >= 16 * (p + 1) && tid < TS) {
+            double s = ybuf[tid];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s = fma(-L[tidx(tid, 16 * p + k)], tmp[k], s);
+            ybuf[tid] = s;
+        }
+    }
+    __syncthreads();
 }
 
 // ---- small helpers -----------------------------------------------------------------------------------------------
@@ -359,7 +443,7 @@ __device__ __forceinline__ double tile_row_dot(const double *T, const double *v,
     return s;
 }
 
-// deterministic block-wide sum (256 threads), result valid in every thread; red = 8 doubles of shared memory
+// deterministic block-wide sum, result valid in every thread; red = NWARPS doubles of shared memory
 __device__ __forceinline__ double block_sum(double v, double *red, int tid) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -368,7 +452,7 @@ __device__ __forceinline__ double block_sum(double v, double *red, int tid) {
     __syncthreads();
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < NTHREADS / 32; ++i) s += red[i];
+    for (int i = 0; i < NWARPS; ++i) s += red[i];
     return s;
 }
 
