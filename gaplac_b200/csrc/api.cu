@@ -441,6 +441,25 @@ int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const doub
     return GPL_OK;
 }
 
+// Debug (profile builds only, -DGPL_LML_PROFILE): run the plain lml kernel with `raw` (device, grid*8 doubles)
+// receiving per-CTA phase clock totals.  Not part of the public header.
+int gpl_debug_phase_profile(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *dX, const double *dY,
+                            const double *dTheta, int p, const double *dsigma2, int B, double *dlml, int *dinfo,
+                            double *raw, int *grid_out) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    // want_grad = 0 but dtheta carries the raw buffer
+    int rc = launch_lml(ctx, prog->dev, n, d, dX, 0, dY, 0, dTheta, p, dsigma2, 0, 0.0, B, dlml, raw, nullptr, dinfo, 0, 0,
+                        nullptr, nullptr, ctx->stream);
+    if (grid_out) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lml_batched_kernel, NTHREADS, lml_smem_bytes(false));
+        *grid_out = ctx->sm_count * occ < B ? ctx->sm_count * occ : B;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
 // ---- posterior ---------------------------------------------------------------------------------------------------
 int gpl_posterior_free(gpl_post *post) {
     if (!post) return GPL_OK;

@@ -173,14 +173,23 @@ template <bool SAME>
 __device__ __forceinline__ void eval_block_acc(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
                                                int lda, int na, const int (&gi)[2], const double *__restrict__ Xb,
                                                int ldb, int nb, int cbase, int t, double diag_add,
-                                               double (&out)[2][16]) {
+                                               double (&out)[2][16], int hmax = 4) {
+    // hmax: quarters h >= hmax (16 columns each) are not evaluated and read as 0 (the part of a diagonal tile that
+    // lies above the diagonal for this warp's rows)
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
         int gjh[4];
         double o[2][4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
-        eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+        if (h < hmax) {
+            eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
+        }
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh)
             if (hh == h) {

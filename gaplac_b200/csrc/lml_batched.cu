@@ -24,6 +24,32 @@ namespace {
 #ifndef GPL_LML_CTAS_PER_SM
 #define GPL_LML_CTAS_PER_SM 4
 #endif
+#ifndef GPL_LML_ZMAX
+#define GPL_LML_ZMAX 1024  // rows of z kept in shared memory (8 KiB)
+#endif
+#ifndef GPL_LML_STREAM_TRSM
+#define GPL_LML_STREAM_TRSM 1  // 1: stream L_jj through the load pipeline; 0: re-load the whole tile, then solve
+#endif
+// Optional phase timers (build with -DGPL_LML_PROFILE): thread 0 of every CTA accumulates clock64() deltas per phase
+// into prm.dtheta (reused as a raw buffer of gridDim.x * 8 doubles).  tools/phase_profile.py reads them.
+#ifdef GPL_LML_PROFILE
+#define PH_DECL long long ph_t0 = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PH_MARK(k)                         \
+    do {                                   \
+        const long long ph_t1 = clock64(); \
+        ph_acc[k] += ph_t1 - ph_t0;        \
+        ph_t0 = ph_t1;                     \
+    } while (0)
+#define PH_DUMP                                                                                         \
+    do {                                                                                                \
+        if (tid == 0 && prm.dtheta)                                                                     \
+            for (int k = 0; k < 8; ++k) prm.dtheta[(size_t)blockIdx.x * 8 + k] = (double)ph_acc[k];      \
+    } while (0)
+#else
+#define PH_DECL
+#define PH_MARK(k)
+#define PH_DUMP
+#endif
 constexpr int LKC = 16;        // columns per pipeline stage
 constexpr int LCH = LKC * TS;  // doubles per operand stage: two stages x (row + column operand) = the 32 KiB buffer S
 static_assert(4 * LCH == TILE_ELEMS, "two stages of both operands fill the staging buffer exactly");
@@ -40,6 +66,7 @@ struct __align__(16) LmlSmem {
     double S[TILE_ELEMS];
     double Bt[GRAD ? TILE_ELEMS : 2];
     double D[DSIZE];  // inverses of the four 16 x 16 diagonal blocks of the current diagonal tile
+    double zs[GPL_LML_ZMAX];  // z = L^-1 y of the current item (global workspace instead when n is larger)
     ItemScalars sc;
     double rsbuf[16];
     double pivbuf[TS];
@@ -67,7 +94,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LmlSmem<GRAD> &sm = *reinterpret_cast<LmlSmem<GRAD> *>(smem_raw);
     const DevProgram &P = prm.prog;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const TMap tm = thread_map(tid);
     const int n = prm.n, nt = prm.nt;
     const long long ntri = tri_index(nt, 0);
@@ -75,9 +102,11 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     double *wsL = prm.ws + (size_t)blockIdx.x * prm.ws_stride;  // lower tiles of L
     double *wsW = wsL + ntri * TILE_ELEMS;                      // inverses of the diagonal tiles
     double *wsM = wsW + (size_t)nt * TILE_ELEMS;                // (L^-1)' tiles (gradient only)
-    double *wsZ = prm.vec + (size_t)blockIdx.x * 2 * nt * TS;   // z = L^-1 y
-    double *wsAl = wsZ + (size_t)nt * TS;                       // alpha = K^-1 y
+    double *wsZg = prm.vec + (size_t)blockIdx.x * 2 * nt * TS;  // z = L^-1 y (global copy: alpha phase, large n)
+    double *wsZ = (nt * TS <= GPL_LML_ZMAX) ? sm.zs : wsZg;
+    double *wsAl = wsZg + (size_t)nt * TS;                      // alpha = K^-1 y
 
+    PH_DECL;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -88,7 +117,10 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
         if (tid < GPL_MAX_THETA) sm.gsum[tid] = 0.0;
         __syncthreads();
         const int b = sm.item;
-        if (b >= prm.B) break;
+        if (b >= prm.B) {
+            PH_DUMP;
+            break;
+        }
         const double *X = prm.X + (size_t)b * prm.x_stride;
         const double *Y = prm.Y + (size_t)b * prm.y_stride;
         const double *theta = prm.Theta + (size_t)b * prm.p;
@@ -99,51 +131,63 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
         for (int j = 0; j < nt; ++j) {
             for (int i = j; i < nt; ++i) {
                 const bool diag = (i == j);
-                const int Q = (TS / LKC) * j;  // pipeline steps: LKC columns of L_ik / L_jk each, k = 0..j-1
+                const int Q = (TS / LKC) * j;   // update steps: LKC columns of L_ik / L_jk each, k = 0..j-1
+                const int QT = (diag || !GPL_LML_STREAM_TRSM) ? Q : Q + 3;  // + 3 steps streaming L_jj for the solve
                 const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1) are contiguous
-                const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;
+                const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1), then L_jj itself
+                // one load pipeline for the whole tile: step s < Q stages 16 columns of both operands of the
+                // update; step Q + q stages columns 16q.. of L_jj (they follow tile (j, j-1) in the workspace)
+                auto issue = [&](int s) {
+                    const int st = (s & 1) * LCH;
+                    if (s < Q) block_load_async<LCH * 8>(sm.S + st, srcA + (size_t)s * LCH, tid);
+                    if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH + st, srcB + (size_t)s * LCH, tid);
+                    cp_async_commit();
+                };
+                (void)QT;
                 // all readers of S (previous tile) are done: start the first loads, then generate the covariance
                 // tile while they are in flight
+                PH_MARK(7);
                 __syncthreads();
-                if (Q > 0) {
-                    block_load_async<LCH * 8>(sm.S, srcA, tid);
-                    if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH, srcB, tid);
-                    cp_async_commit();
-                }
+                PH_MARK(0);
+                if (QT > 0) issue(0);
                 double acc[2][NCC];
                 {
                     int gi[2];
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
-                    eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc);
+                    // a diagonal tile is only needed on and below the diagonal: warp w (rows 16w..) skips the 16-column
+                    // quarters h > w here and the n-blocks nb > 2w + 1 in its update loop
+                    eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, diag ? warp + 1 : 4);
                 }
+                PH_MARK(1);
                 double ytmp = 0.0;
                 if (diag && tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
                 for (int q = 0; q < Q; ++q) {
                     cp_async_wait<0>();
                     __syncthreads();  // step q landed for everyone; everyone finished step q-1
-                    if (q + 1 < Q) {
-                        const int nb = ((q + 1) & 1) * LCH;
-                        block_load_async<LCH * 8>(sm.S + nb, srcA + (size_t)(q + 1) * LCH, tid);
-                        if (!diag) block_load_async<LCH * 8>(sm.S + 2 * LCH + nb, srcB + (size_t)(q + 1) * LCH, tid);
-                        cp_async_commit();
-                    }
+                    if (q + 1 < QT) issue(q + 1);
                     // 16 whole columns starting at a multiple of 4 are themselves in tile format (swizzle uses c & 3)
                     const double *a = sm.S + (q & 1) * LCH;
-                    const double *bt = diag ? a : a + 2 * LCH;
-                    tile_mma<true>(acc, a, bt, tm, 0, LKC);
+                    const double *bt = a + 2 * LCH;
+                    if (diag) tile_mma<true, 0xFF, true>(acc, a, a, tm, 0, LKC, 2 * warp + 2);
+                    else tile_mma<true>(acc, a, bt, tm, 0, LKC);
                     if (diag && tid < TS) ytmp -= tile_row_dot(a, wsZ + q * LKC, tid, 0, LKC);
                 }
+                PH_MARK(2);
                 if (diag) {
                     __syncthreads();  // S becomes the factorisation scratch
                     const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+                    PH_MARK(3);
                     if (tid == 0 && fail >= 0 && sm.info == 0) sm.info = j * TS + fail + 1;
                     acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
                     __syncthreads();  // scratch no longer read
-                    acc_to_tile(sm.S, acc, tm);  // L_jj stays in S for the forward solve (and, for column 0, the solves below)
+                    acc_to_tile(sm.S, acc, tm);  // L_jj in shared memory for the forward solve (and the inverse)
                     if (tid < TS) sm.ybuf[tid] = ytmp;
                     tile_forward_solve(sm.S, sm.D, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
-                    if (tid < TS) wsZ[j * TS + tid] = sm.ybuf[tid];
+                    if (tid < TS) {
+                        wsZ[j * TS + tid] = sm.ybuf[tid];
+                        if (wsZ != wsZg && (prm.want_grad || prm.keep)) wsZg[j * TS + tid] = sm.ybuf[tid];
+                    }
                     if (tid < 32) {
                         double lg = log(sm.pivbuf[tid]) + log(sm.pivbuf[tid + 32]);
 #pragma unroll
@@ -160,18 +204,38 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                         tile_trsm_ld(e, sm.S, sm.D, tm);
                         acc_to_tile_t(wsW + (size_t)j * TILE_ELEMS, e, tm);
                     }
+                    PH_MARK(4);
                 } else {
-                    // L_ij = T_ij L_jj^-T: row operand from the accumulator registers; L_jj re-loaded into S (it is
-                    // still there for column 0, whose tiles have no update loop); its block inverses are still in D
-                    if (Q > 0) {
-                        __syncthreads();
-                        tile_load_async(sm.S, wsL + tri_index(j, j) * TILE_ELEMS, tid);
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                        __syncthreads();
-                    }
+                    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels: the row operands come from
+                    // the accumulator registers, the block inverses from D (still there from the diagonal tile), and
+                    // the columns of L_jj arrive through the same pipeline (steps Q, Q+1, Q+2; Q is even)
+#if !GPL_LML_STREAM_TRSM
+                    __syncthreads();
+                    tile_load_async(sm.S, wsL + tri_index(j, j) * TILE_ELEMS, tid);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    __syncthreads();
                     tile_trsm_ld(acc, sm.S, sm.D, tm);
+#else
+                    trsm_rl_solve<0>(acc, sm.D, tm);
+                    cp_async_wait<0>();
+                    __syncthreads();
+                    issue(Q + 1);
+                    trsm_rl_update<0>(acc, sm.S + 2 * LCH, tm);
+                    trsm_rl_solve<1>(acc, sm.D, tm);
+                    cp_async_wait<0>();
+                    __syncthreads();
+                    issue(Q + 2);
+                    trsm_rl_update<1>(acc, sm.S + 3 * LCH, tm);
+                    trsm_rl_solve<2>(acc, sm.D, tm);
+                    cp_async_wait<0>();
+                    __syncthreads();
+                    trsm_rl_update<2>(acc, sm.S + 2 * LCH, tm);
+                    trsm_rl_solve<3>(acc, sm.D, tm);
+#endif
+                    PH_MARK(5);
                     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
+                    PH_MARK(6);
                 }
             }
         }

@@ -123,11 +123,12 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// acc (+|-)= A[rows, k0:k1] * B[cols, k0:k1]'   for the n-blocks nb with (NBMASK >> nb) & 1 (8 columns each).
+// acc (+|-)= A[rows, k0:k1] * B[cols, k0:k1]'   for the n-blocks nb with (NBMASK >> nb) & 1 (8 columns each); with
+// LIMIT additionally only nb < nbmax (warp-uniform run-time bound: diagonal tiles skip the blocks above the diagonal).
 // k0, k1 multiples of 4.  A and B are tiles (or runs of whole columns starting at a multiple of 4) in tile format.
-template <bool SUB, int NBMASK = 0xFF>
+template <bool SUB, int NBMASK = 0xFF, bool LIMIT = false>
 __device__ __forceinline__ void tile_mma(double (&acc)[2][NCC], const double *__restrict__ A,
-                                         const double *__restrict__ B, const TMap &tm, int k0, int k1) {
+                                         const double *__restrict__ B, const TMap &tm, int k0, int k1, int nbmax = 8) {
     // (k + t) & 3 == t for k % 4 == 0: the swizzle is a per-lane constant.  For the column operand the row index is
     // 8 nb + g: xor with sw = 4t flips bit 2 of g and (for t >= 2) bit 3, i.e. swaps odd and even n-blocks.
     const int sw = tm.t << 2;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][NCC], const double *__
         }
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            if ((NBMASK >> nb) & 1) {
+            if (((NBMASK >> nb) & 1) && (!LIMIT || nb < nbmax)) {
                 const double b = ((nb & 1) ? pbo : pbe)[k * TS + 16 * (nb >> 1)];
                 dmma884(acc[0][2 * nb], acc[0][2 * nb + 1], a0, b);
                 dmma884(acc[1][2 * nb], acc[1][2 * nb + 1], a1, b);
@@ -396,6 +397,47 @@ __device__ __forceinline__ void tile_trsm_ld(double (&acc)[2][NCC], const double
     trsm_ld_panel<1>(acc, L, D, tm);
     trsm_ld_panel<2>(acc, L, D, tm);
     trsm_ld_panel<3>(acc, L, D, tm);
+}
+
+// Right-looking variant of the same solve, split so that the caller can stream L through a load pipeline 16 columns
+// at a time:  for q = 0..3:  trsm_rl_solve<q> (X_q = T_q W16_q', registers and D only), then trsm_rl_update<q> with the
+// chunk L[:, 16q .. 16q+15] (tile format, 64 x 16) to apply  T_p -= X_q L_pq'  to every later panel p > q.
+template <int Q_>
+__device__ __forceinline__ void trsm_rl_solve(double (&acc)[2][NCC], const double *__restrict__ D, const TMap &tm) {
+    const double *W16 = D + Q_ * DBLK;
+    double x[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int kl = 0; kl < 4; ++kl) {
+        double a[2];
+        acc_a_frag(acc, 4 * Q_ + kl, tm, a);
+#pragma unroll
+        for (int nbl = kl >> 1; nbl < 2; ++nbl) {
+            const double b = W16[(8 * nbl + tm.g) * DLD + 4 * kl + tm.t];
+            dmma884(x[0][2 * nbl], x[0][2 * nbl + 1], a[0], b);
+            dmma884(x[1][2 * nbl], x[1][2 * nbl + 1], a[1], b);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mb][4 * Q_ + q] = x[mb][q];
+}
+template <int Q_>
+__device__ __forceinline__ void trsm_rl_update(double (&acc)[2][NCC], const double *__restrict__ chunk, const TMap &tm) {
+    const int sw = tm.t << 2;
+    const double *pbe = chunk + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);        // even n-blocks
+    const double *pbo = chunk + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));  // odd n-blocks
+#pragma unroll
+    for (int kl = 0; kl < 4; ++kl) {
+        double a[2];
+        acc_a_frag(acc, 4 * Q_ + kl, tm, a);
+#pragma unroll
+        for (int nb = 2 * (Q_ + 1); nb < 8; ++nb) {
+            const double b = ((nb & 1) ? pbo : pbe)[4 * kl * TS + 16 * (nb >> 1)];
+            dmma884(acc[0][2 * nb], acc[0][2 * nb + 1], -a[0], b);
+            dmma884(acc[1][2 * nb], acc[1][2 * nb + 1], -a[1], b);
+        }
+    }
 }
 
 // z = L^-1 y for one 64-vector, all threads of the CTA (four block steps, two barriers each):
