@@ -42,8 +42,10 @@ struct gpl_ctx {
     std::mutex mu;
     int lml_variant = 0;
     int chol_variant = 0;
-    bool attr_lml = false, attr_big = false, attr_pred = false;
+    bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false;
+    size_t lk_ws_limit = (size_t)12 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
     // grow-only device buffers
+    DevBuf lkTiles, lkD, lkZ, lkAcc;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
 };
 
@@ -107,10 +109,16 @@ int check_prog_args(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, int p) {
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------------------
+int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
+                        const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
+                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st);
 int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched, const double *dY,
                int y_batched, const double *dTheta, int p, const double *dsigma2, int sigma2_batched, double jitter,
                int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
                double *keep_ws, double *keep_vec, cudaStream_t st) {
+    if (!want_grad && !keep && ctx->lml_variant != 1)
+        return launch_lml_lockstep(ctx, prog, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
+                                   dlml, dinfo, st);
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     const long long tiles_per_cta = ntri + nt + (want_grad ? ntri : 0);
@@ -170,6 +178,76 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     if (want_grad) lml_batched_grad_kernel<<<grid, NTHREADS, smem, st>>>(prm);
     else lml_batched_kernel<<<grid, NTHREADS, smem, st>>>(prm);
     ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return GPL_OK;
+}
+
+// lockstep schedule for plain log-likelihoods (no gradient, nothing kept): 3 kernels per tile column over the batch
+int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
+                        const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
+                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st) {
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    if (!ctx->attr_lk) {
+        CU(ctx, cudaFuncSetAttribute(lk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_below_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_potrf_smem_bytes()));
+        ctx->attr_lk = true;
+    }
+    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16;
+    int Bc = (int)(ctx->lk_ws_limit / per_item);
+    if (Bc < 1) Bc = 1;
+    if (Bc > B) Bc = B;
+    int rc;
+    if ((rc = ensure(ctx, ctx->lkTiles, (size_t)Bc * ntri * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkD, (size_t)Bc * nt * DSIZE * 8)) ||
+        (rc = ensure(ctx, ctx->lkZ, (size_t)Bc * nt * TS * 8)) || (rc = ensure(ctx, ctx->lkAcc, (size_t)Bc * 16)))
+        return rc;
+    int *info_dev = dinfo;
+    if (!info_dev) {
+        if ((rc = ensure(ctx, ctx->bInfo, (size_t)B * 4))) return rc;
+        info_dev = ptr<int>(ctx->bInfo);
+    }
+    CU(ctx, cudaMemsetAsync(info_dev, 0, (size_t)B * sizeof(int), st));
+    LkParams prm;
+    prm.prog = prog;
+    prm.n = n;
+    prm.d = d;
+    prm.nt = nt;
+    prm.p = p;
+    prm.sigma2_stride = sigma2_batched ? 1 : 0;
+    prm.x_stride = x_batched ? (long long)n * d : 0;
+    prm.y_stride = y_batched ? n : 0;
+    prm.jitter = jitter;
+    prm.tiles = ptr<double>(ctx->lkTiles);
+    prm.dblk = ptr<double>(ctx->lkD);
+    prm.z = ptr<double>(ctx->lkZ);
+    LkPotrfParams pp;
+    pp.n = n;
+    pp.nt = nt;
+    pp.tiles = prm.tiles;
+    pp.dblk = prm.dblk;
+    pp.z = prm.z;
+    pp.acc2 = ptr<double>(ctx->lkAcc);
+    for (int off = 0; off < B; off += Bc) {
+        const int nb = (B - off < Bc) ? B - off : Bc;
+        prm.X = dX + (size_t)off * prm.x_stride;
+        prm.Y = dY + (size_t)off * prm.y_stride;
+        prm.Theta = dTheta + (size_t)off * p;
+        prm.sigma2 = dsigma2 + (size_t)off * prm.sigma2_stride;
+        pp.lml = dlml + off;
+        pp.info = info_dev + off;
+        for (int j = 0; j < nt; ++j) {
+            prm.j = j;
+            pp.j = j;
+            lk_diag_kernel<<<nb, NTHREADS, lk_step_smem_bytes(), st>>>(prm);
+            lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);
+            ctx->launches += 2;
+            if (j + 1 < nt) {
+                lk_below_kernel<<<(unsigned)((size_t)nb * (nt - 1 - j)), NTHREADS, lk_step_smem_bytes(), st>>>(prm);
+                ctx->launches++;
+            }
+        }
+    }
     CU(ctx, cudaGetLastError());
     return GPL_OK;
 }
@@ -285,7 +363,7 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    DevBuf *bufs[] = {&ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
@@ -301,6 +379,7 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return fail(ctx, GPL_ERR_ARG, "gpl_set_option: null argument");
     if (!strcmp(key, "lml_variant")) ctx->lml_variant = value;
     else if (!strcmp(key, "chol_variant")) ctx->chol_variant = value;
+    else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
     else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
     return GPL_OK;
 }

@@ -27,6 +27,34 @@ __global__ void lml_batched_kernel(const __grid_constant__ LmlParams prm);      
 __global__ void lml_batched_grad_kernel(const __grid_constant__ LmlParams prm);  // lml + gradient: 2 CTAs / SM
 size_t lml_smem_bytes(bool grad);
 
+// ---- batched lml, lockstep schedule (lml_lockstep.cu): three kernels per tile column over the whole batch ------------
+#ifndef GPL_LK_ZMAX
+#define GPL_LK_ZMAX 1024  // rows of z staged in shared memory by the diagonal-tile kernel
+#endif
+struct LkParams {
+    DevProgram prog;
+    int n, d, nt, p, j;
+    int sigma2_stride;
+    long long x_stride, y_stride;
+    const double *X, *Y, *Theta, *sigma2;
+    double jitter;
+    double *tiles;  // B x ntri tiles (tile-major lower factor of every item)
+    double *dblk;   // B x nt x DSIZE: block inverses of the diagonal tiles
+    double *z;      // B x nt*64: right-hand side / z = L^-1 y
+};
+struct LkPotrfParams {
+    int n, nt, j;
+    double *tiles, *dblk, *z;
+    double *acc2;  // B x 2: running z'z and logdet
+    double *lml;
+    int *info;
+};
+__global__ void lk_diag_kernel(const __grid_constant__ LkParams prm);        // grid B
+__global__ void lk_potrf_kernel(const __grid_constant__ LkPotrfParams prm);  // grid B
+__global__ void lk_below_kernel(const __grid_constant__ LkParams prm);       // grid B * (nt - 1 - j)
+size_t lk_step_smem_bytes();
+size_t lk_potrf_smem_bytes();
+
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
 struct CovParams {
     DevProgram prog;

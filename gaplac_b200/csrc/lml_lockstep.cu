@@ -1,0 +1,226 @@
+// Batched log-marginal-likelihood, "lockstep" schedule: all GPs of the batch advance tile column by tile column
+// through three kernels per column, so that the latency-bound pivot chains of the diagonal tiles never share an SM
+// sub-partition with streams of tensor instructions.
+//
+// Why not one fused kernel per GP (lml_batched.cu)?  Measured on B200 (tools/pipe_mix.cu, profiles/README.md): a
+// warp issuing dependent FP64 operations slows from 8 to 73 clocks per operation when ONE other warp on its SM
+// sub-partition streams DMMAs, and is starved outright (2*10^4 clocks per operation) by two of them.  In the fused
+// kernel the diagonal-tile Cholesky of one GP (64 sequential pivots per tile) ran exactly in that situation next to
+// the update loops of its three co-resident GPs: 19 % of every CTA's life went into 8 % of its arithmetic.
+//
+// Replaces, per batch item, logpdf(FiniteGP, y) [upstream AbstractGPs 0.5.12]: kernelmatrix -> + sigma2 I ->
+// cholesky (dpotrf) -> U' \ y (dtrtrs) -> logdet; call sites CLI/src/select.jl:49-50, CLI/src/mcmc.jl:35.
+//
+// Per tile column j (left-looking blocked Cholesky on 64 x 64 tiles, workspace = every item's lower tiles in HBM):
+//   lk_diag_kernel   grid B          T_jj = K_jj - sum_k L_jk L_jk'   (covariance tile generated in registers, DMMA
+//                                    update from the streamed tiles), y_j - sum_k L_jk z_k
+//   lk_potrf_kernel  grid B          L_jj = chol(T_jj), its four 16 x 16 block inverses, z_j, logdet and z'z partial sums
+//   lk_below_kernel  grid B*(nt-1-j) L_ij = (K_ij - sum_k L_ik L_jk') L_jj^-T   (K-gen, DMMA update, streamed solve)
+// The first and third kernel are pure throughput kernels (every phase saturates the FP64 pipe); the second is
+// latency-bound but runs thousands of independent chains with nothing else on the machine.
+#include "kernels.h"
+#include "kfun.cuh"
+#include "tile.cuh"
+
+namespace gpl {
+
+namespace {
+
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+constexpr int LKC = 16;        // columns per pipeline stage
+constexpr int LCH = LKC * TS;  // doubles per operand stage; S = two stages of both operands = 32 KiB
+static_assert(4 * LCH == TILE_ELEMS, "two stages of both operands fill the staging buffer exactly");
+
+struct __align__(16) StepSmem {
+    double S[TILE_ELEMS];
+    double D[DSIZE];
+    ItemScalars sc;
+    double zs[GPL_LK_ZMAX];  // z_k of the earlier tile columns (diag kernel)
+};
+
+struct __align__(16) PotrfSmem {
+    double S[TILE_ELEMS];
+    double D[DSIZE];
+    double rsbuf[16];
+    double pivbuf[TS];
+    double ybuf[TS];
+    double tmp16[16];
+    double L16s[256];
+    double red[NWARPS];
+};
+
+__device__ __forceinline__ const double *item_ptr(const double *base, long long stride, int b) {
+    return base + (size_t)b * stride;
+}
+
+}  // namespace
+
+size_t lk_step_smem_bytes() { return sizeof(StepSmem); }
+size_t lk_potrf_smem_bytes() { return sizeof(PotrfSmem); }
+
+// ---- diagonal tile of column j: covariance + update, right-hand side update ----------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_constant__ LkParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem &sm = *reinterpret_cast<StepSmem *>(smem_raw);
+    const DevProgram &P = prm.prog;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const TMap tm = thread_map(tid);
+    const int n = prm.n, nt = prm.nt, j = prm.j, b = blockIdx.x;
+    const long long ntri = tri_index(nt, 0);
+    double *wsL = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
+    double *zb = prm.z + (size_t)b * nt * TS;
+    const double *X = item_ptr(prm.X, prm.x_stride, b);
+    const double *Y = item_ptr(prm.Y, prm.y_stride, b);
+    const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
+    prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
+
+    const int Q = (TS / LKC) * j;
+    const double *srcA = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1) are contiguous
+    auto issue = [&](int s) {
+        block_load_async<LCH * 8>(sm.S + (s & 1) * LCH, srcA + (size_t)s * LCH, tid);
+        cp_async_commit();
+    };
+    const bool z_in_smem = j * TS <= GPL_LK_ZMAX;
+    if (z_in_smem)
+        for (int t = tid; t < j * TS; t += NTHREADS) sm.zs[t] = zb[t];
+    const double *zsrc = z_in_smem ? sm.zs : zb;
+    if (Q > 0) issue(0);
+    __syncthreads();  // item scalars, z
+    double acc[2][NCC];
+    {
+        int gi[2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) gi[mb] = j * TS + row_of(tm, mb);
+        // only the part on and below the diagonal is needed: warp w (rows 16w..) skips the 16-column quarters h > w
+        // here and the n-blocks nb > 2w + 1 in its update loop
+        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, warp + 1);
+    }
+    double ytmp = 0.0;
+    if (tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
+    for (int q = 0; q < Q; ++q) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (q + 1 < Q) issue(q + 1);
+        const double *a = sm.S + (q & 1) * LCH;
+        tile_mma<true, 0xFF, true>(acc, a, a, tm, 0, LKC, 2 * warp + 2);
+        if (tid < TS) ytmp -= tile_row_dot(a, zsrc + q * LKC, tid, 0, LKC);
+    }
+    acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
+    if (tid < TS) zb[j * TS + tid] = ytmp;
+}
+
+// ---- Cholesky of the diagonal tiles of column j -----------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 4) lk_potrf_kernel(const __grid_constant__ LkPotrfParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const TMap tm = thread_map(tid);
+    const int nt = prm.nt, j = prm.j, b = blockIdx.x;
+    const long long ntri = tri_index(nt, 0);
+    double *Tjj = prm.tiles + ((size_t)b * ntri + tri_index(j, j)) * TILE_ELEMS;
+    double *zb = prm.z + (size_t)b * nt * TS;
+    tile_load_async(sm.S, Tjj, tid);
+    cp_async_commit();
+    if (tid < TS) sm.ybuf[tid] = zb[j * TS + tid];
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][NCC];
+    acc_from_tile(acc, sm.S, tm);
+    __syncthreads();  // S becomes the factorisation scratch
+    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+    if (tid == 0 && fail >= 0 && prm.info[b] == 0) prm.info[b] = j * TS + fail + 1;
+    acc_to_tile(Tjj, acc, tm);
+    __syncthreads();  // scratch no longer read
+    acc_to_tile(sm.S, acc, tm);
+    tile_forward_solve(sm.S, sm.D, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
+    double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
+    for (int t = tid; t < DSIZE; t += NTHREADS) Dg[t] = sm.D[t];
+    double zq = 0.0, lg = 0.0;
+    if (tid < TS) {
+        const double z = sm.ybuf[tid];
+        zb[j * TS + tid] = z;
+        zq = z * z;
+        lg = log(sm.pivbuf[tid]);
+    }
+    zq = block_sum(zq, sm.red, tid);
+    lg = block_sum(lg, sm.red, tid);
+    if (tid == 0) {
+        const double q = (j ? prm.acc2[2 * b] : 0.0) + zq, l = (j ? prm.acc2[2 * b + 1] : 0.0) + lg;
+        prm.acc2[2 * b] = q;
+        prm.acc2[2 * b + 1] = l;
+        if (j == nt - 1) {
+            const int inf = prm.info[b];
+            prm.lml[b] = inf ? -INFINITY : -0.5 * ((double)prm.n * LOG2PI + l + q);
+        }
+    }
+}
+
+// ---- tiles below the diagonal of column j -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_constant__ LkParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem &sm = *reinterpret_cast<StepSmem *>(smem_raw);
+    const DevProgram &P = prm.prog;
+    const int tid = threadIdx.x;
+    const TMap tm = thread_map(tid);
+    const int n = prm.n, nt = prm.nt, j = prm.j;
+    const int nbelow = nt - 1 - j;
+    const int b = blockIdx.x / nbelow, i = j + 1 + blockIdx.x % nbelow;  // the tiles of one GP are neighbours (L2 reuse)
+    const long long ntri = tri_index(nt, 0);
+    double *wsL = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
+    const double *X = item_ptr(prm.X, prm.x_stride, b);
+    const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
+    prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
+
+    const int Q = (TS / LKC) * j;   // update steps
+    const int QT = Q + 3;           // + 3 steps streaming columns of L_jj for the triangular solve
+    const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1)
+    const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1), then L_jj itself
+    auto issue = [&](int s) {
+        const int st = (s & 1) * LCH;
+        if (s < Q) block_load_async<LCH * 8>(sm.S + st, srcA + (size_t)s * LCH, tid);
+        block_load_async<LCH * 8>(sm.S + 2 * LCH + st, srcB + (size_t)s * LCH, tid);
+        cp_async_commit();
+    };
+    // block inverses of L_jj ride in the first commit group
+    {
+        const double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
+        static_assert(DSIZE * 8 % (16 * NTHREADS) == 0, "D in whole 16-byte chunks per thread");
+        block_load_async<DSIZE * 8>(sm.D, Dg, tid);
+    }
+    issue(0);
+    __syncthreads();  // item scalars
+    double acc[2][NCC];
+    {
+        int gi[2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
+        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc);
+    }
+    for (int q = 0; q < Q; ++q) {
+        cp_async_wait<0>();
+        __syncthreads();
+        issue(q + 1);  // q + 1 <= Q < QT always
+        const double *a = sm.S + (q & 1) * LCH;
+        tile_mma<true>(acc, a, a + 2 * LCH, tm, 0, LKC);
+    }
+    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels (Q is even: stage parity = q & 1)
+    cp_async_wait<0>();
+    __syncthreads();  // step Q (and D) landed
+    issue(Q + 1);
+    trsm_rl_solve<0>(acc, sm.D, tm);
+    trsm_rl_update<0>(acc, sm.S + 2 * LCH, tm);
+    trsm_rl_solve<1>(acc, sm.D, tm);
+    cp_async_wait<0>();
+    __syncthreads();
+    issue(Q + 2);
+    trsm_rl_update<1>(acc, sm.S + 3 * LCH, tm);
+    trsm_rl_solve<2>(acc, sm.D, tm);
+    cp_async_wait<0>();
+    __syncthreads();
+    trsm_rl_update<2>(acc, sm.S + 2 * LCH, tm);
+    trsm_rl_solve<3>(acc, sm.D, tm);
+    acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
+    (void)QT;
+}
+
+}  // namespace gpl
