@@ -59,6 +59,31 @@ size_t lk_step_smem_bytes() { return sizeof(StepSmem); }
 size_t lk_potrf_smem_bytes() { return sizeof(PotrfSmem); }
 
 // ---- diagonal tile of column j: covariance + update, right-hand side update ----------------------------------------
+// Only the lower triangle of a diagonal tile is needed (36 of its 64 8 x 8 blocks).  To balance them over the four
+// warps this kernel uses its own row map: warp w owns row block w (accumulator row 0, needs n-blocks 0..w) and row
+// block 7 - w (accumulator row 1, needs n-blocks 0..7-w): 9 blocks per warp.  The potrf kernel re-loads the tile in
+// the standard map, so nothing else sees this layout.
+template <int W>
+__device__ __forceinline__ void diag_mma(double (&acc)[2][NCC], const double *__restrict__ A, const TMap &tm) {
+    const int sw = tm.t << 2;
+    const double *pa0 = A + tm.t * TS + ((8 * W + tm.g) ^ sw);
+    const double *pa1 = A + tm.t * TS + ((8 * (7 - W) + tm.g) ^ sw);
+    const double *pbe = A + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);
+    const double *pbo = A + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+        const double a0 = -pa0[k * TS], a1 = -pa1[k * TS];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            if (nb <= W || nb <= 7 - W) {
+                const double b = ((nb & 1) ? pbo : pbe)[k * TS + 16 * (nb >> 1)];
+                if (nb <= W) dmma884(acc[0][2 * nb], acc[0][2 * nb + 1], a0, b);
+                if (nb <= 7 - W) dmma884(acc[1][2 * nb], acc[1][2 * nb + 1], a1, b);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_constant__ LkParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem &sm = *reinterpret_cast<StepSmem *>(smem_raw);
@@ -86,14 +111,12 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
     const double *zsrc = z_in_smem ? sm.zs : zb;
     if (Q > 0) issue(0);
     __syncthreads();  // item scalars, z
+    const int rows[2] = {8 * warp + tm.g, 8 * (7 - warp) + tm.g};  // this kernel's row map
     double acc[2][NCC];
     {
-        int gi[2];
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) gi[mb] = j * TS + row_of(tm, mb);
-        // only the part on and below the diagonal is needed: warp w (rows 16w..) skips the 16-column quarters h > w
-        // here and the n-blocks nb > 2w + 1 in its update loop
-        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, warp + 1);
+        int gi[2] = {j * TS + rows[0], j * TS + rows[1]};
+        // quarters of 16 columns: row block 7 - w needs columns up to 63 - 8w
+        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, (63 - 8 * warp) / 16 + 1);
     }
     double ytmp = 0.0;
     if (tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
@@ -102,10 +125,19 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
         __syncthreads();
         if (q + 1 < Q) issue(q + 1);
         const double *a = sm.S + (q & 1) * LCH;
-        tile_mma<true, 0xFF, true>(acc, a, a, tm, 0, LKC, 2 * warp + 2);
+        switch (warp) {
+        case 0: diag_mma<0>(acc, a, tm); break;
+        case 1: diag_mma<1>(acc, a, tm); break;
+        case 2: diag_mma<2>(acc, a, tm); break;
+        default: diag_mma<3>(acc, a, tm); break;
+        }
         if (tid < TS) ytmp -= tile_row_dot(a, zsrc + q * LKC, tid, 0, LKC);
     }
-    acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
+    double *Tjj = wsL + tri_index(j, j) * TILE_ELEMS;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int cc = 0; cc < NCC; ++cc) Tjj[tidx(rows[mb], col_of(tm, cc))] = acc[mb][cc];
     if (tid < TS) zb[j * TS + tid] = ytmp;
 }
 
@@ -127,8 +159,10 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_potrf_kernel(const __grid_cons
     double acc[2][NCC];
     acc_from_tile(acc, sm.S, tm);
     __syncthreads();  // S becomes the factorisation scratch
-    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
-    if (tid == 0 && fail >= 0 && prm.info[b] == 0) prm.info[b] = j * TS + fail + 1;
+    const int cw = b & (NWARPS - 1);  // spread the pivot chains of co-resident CTAs over the SM sub-partitions
+    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid, cw);
+    if (tid == cw * 32 && fail >= 0 && prm.info[b] == 0) prm.info[b] = j * TS + fail + 1;
+    __syncthreads();  // info[b] is read again below by thread 0
     acc_to_tile(Tjj, acc, tm);
     __syncthreads();  // scratch no longer read
     acc_to_tile(sm.S, acc, tm);
@@ -171,14 +205,22 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
     prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
 
-    const int Q = (TS / LKC) * j;   // update steps
-    const int QT = Q + 3;           // + 3 steps streaming columns of L_jj for the triangular solve
+    const int Q = (TS / LKC) * j;  // update steps (even)
     const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1)
     const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1), then L_jj itself
-    auto issue = [&](int s) {
+    const double *srcL = wsL + tri_index(j, j) * TILE_ELEMS;
+    // The four 8 KiB slots of S: A0 = S, A1 = S + LCH, B0 = S + 2 LCH, B1 = S + 3 LCH.  Update step s uses (A, B)[s & 1].
+    // The triangular solve needs columns 0..47 of L_jj as three chunks: chunk 0 -> B0, chunk 1 -> A0 (both free while the
+    // last update step runs out of A1 / B1), chunk 2 -> B1 once that step is done.
+    auto issue = [&](int s) {  // update step s < Q
         const int st = (s & 1) * LCH;
-        if (s < Q) block_load_async<LCH * 8>(sm.S + st, srcA + (size_t)s * LCH, tid);
+        block_load_async<LCH * 8>(sm.S + st, srcA + (size_t)s * LCH, tid);
         block_load_async<LCH * 8>(sm.S + 2 * LCH + st, srcB + (size_t)s * LCH, tid);
+        cp_async_commit();
+    };
+    auto issue_l01 = [&]() {
+        block_load_async<LCH * 8>(sm.S + 2 * LCH, srcL, tid);
+        block_load_async<LCH * 8>(sm.S, srcL + LCH, tid);
         cp_async_commit();
     };
     // block inverses of L_jj ride in the first commit group
@@ -187,7 +229,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         static_assert(DSIZE * 8 % (16 * NTHREADS) == 0, "D in whole 16-byte chunks per thread");
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
     }
-    issue(0);
+    if (Q > 0) issue(0);
+    else issue_l01();
     __syncthreads();  // item scalars
     double acc[2][NCC];
     {
@@ -199,28 +242,26 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<0>();
         __syncthreads();
-        issue(q + 1);  // q + 1 <= Q < QT always
+        if (q + 1 < Q) issue(q + 1);
+        else issue_l01();  // q = Q - 1 is odd: slots A0 / B0 are free
         const double *a = sm.S + (q & 1) * LCH;
         tile_mma<true>(acc, a, a + 2 * LCH, tm, 0, LKC);
     }
-    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels (Q is even: stage parity = q & 1)
+    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels
     cp_async_wait<0>();
-    __syncthreads();  // step Q (and D) landed
-    issue(Q + 1);
+    __syncthreads();  // chunks 0, 1 (and D) landed; slots A1 / B1 free
+    block_load_async<LCH * 8>(sm.S + 3 * LCH, srcL + 2 * LCH, tid);
+    cp_async_commit();
     trsm_rl_solve<0>(acc, sm.D, tm);
     trsm_rl_update<0>(acc, sm.S + 2 * LCH, tm);
     trsm_rl_solve<1>(acc, sm.D, tm);
-    cp_async_wait<0>();
-    __syncthreads();
-    issue(Q + 2);
-    trsm_rl_update<1>(acc, sm.S + 3 * LCH, tm);
+    trsm_rl_update<1>(acc, sm.S, tm);
     trsm_rl_solve<2>(acc, sm.D, tm);
     cp_async_wait<0>();
     __syncthreads();
-    trsm_rl_update<2>(acc, sm.S + 2 * LCH, tm);
+    trsm_rl_update<2>(acc, sm.S + 3 * LCH, tm);
     trsm_rl_solve<3>(acc, sm.D, tm);
     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
-    (void)QT;
 }
 
 }  // namespace gpl

@@ -215,7 +215,7 @@ __device__ __forceinline__ void tile_trsm_w(double (&acc)[2][NCC], const double 
 // Three block barriers per panel.  The triangular solves that follow (tile_trsm_ld, tile_forward_solve) use L and the
 // four block inverses, so the full 64 x 64 inverse is only formed where a caller needs it (tile_inverse_from_ld).
 // scratch: 2048 doubles (P, Lp: 64 x 16 in tile format); L16s: 256; rsbuf: 16; pivbuf: 64 (pivots, for logdet).
-// Returns (in warp 0) -1 or the local index of the first non-positive pivot.
+// Returns (in the chain warp) -1 or the local index of the first non-positive pivot.
 constexpr int DLD = 20;
 constexpr int DBLK = 16 * DLD;    // 320 doubles per block inverse
 constexpr int DSIZE = 4 * DBLK;   // 1280 doubles = 10 KiB per diagonal tile
@@ -235,7 +235,9 @@ __device__ __forceinline__ void potrf_panel_update(double (&acc)[2][NCC], const 
 }
 
 __device__ __forceinline__ int tile_potrf(double (&acc)[2][NCC], const TMap &tm, double *scratch, double *L16s,
-                                          double *D, double *rsbuf, double *pivbuf, int tid) {
+                                          double *D, double *rsbuf, double *pivbuf, int tid, int chain_warp = 0) {
+    // chain_warp: which warp runs the 16 x 16 pivot chains (callers rotate it over co-resident CTAs so that the
+    // chains of different CTAs land on different SM sub-partitions); its return value carries `fail`
     const int warp = tid >> 5, lane = tid & 31;
     double *P = scratch;         // columns of the panel: element (row, k) at tidx(row, k)
     double *Lp = scratch + 1024; // panel of L, (row, k)
@@ -253,8 +255,8 @@ __device__ __forceinline__ int tile_potrf(double (&acc)[2][NCC], const TMap &tm,
                     for (int q = 0; q < 4; ++q) P[tidx(row_of(tm, mb), col_of(tm, q))] = acc[mb][4 * pp + q];
             }
         __syncthreads();
-        // 2. warp 0: 16 x 16 Cholesky, one row per lane, pivots and columns exchanged with warp shuffles
-        if (warp == 0) {
+        // 2. one warp: 16 x 16 Cholesky, one row per lane, pivots and columns exchanged with warp shuffles
+        if (warp == chain_warp) {
             const int r_own = lane & 15;  // row owned by this lane (lanes 16..31 mirror 0..15)
             double a[16];
 #pragma unroll
