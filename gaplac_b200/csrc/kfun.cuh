@@ -168,36 +168,60 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
 }
 
 // The 2 x 16 accumulator block of one thread (tile.cuh: rows gi[0..1], columns cbase + 8 (cc/2) + 2 t + cc%2) as four
-// 2 x 4 quarters in a rolled loop: one copy of the evaluation code, few live temporaries.
-template <bool SAME>
+// 2 x 4 quarters.  ROLLED = true keeps one copy of the evaluation code (small kernels, instruction-cache bound fused
+// kernel) at the price of select-copies into the dynamically indexed quarter; ROLLED = false unrolls the quarters
+// (static register indices, no copies) for the throughput kernels of the lockstep schedule.
+// hmax: quarters h >= hmax (16 columns each) are not evaluated and read as 0 (the part of a diagonal tile that lies
+// above the diagonal for this warp's rows).
+template <bool SAME, bool ROLLED = true>
 __device__ __forceinline__ void eval_block_acc(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
                                                int lda, int na, const int (&gi)[2], const double *__restrict__ Xb,
                                                int ldb, int nb, int cbase, int t, double diag_add,
                                                double (&out)[2][16], int hmax = 4) {
-    // hmax: quarters h >= hmax (16 columns each) are not evaluated and read as 0 (the part of a diagonal tile that
-    // lies above the diagonal for this warp's rows)
+    if (ROLLED) {
 #pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
-        int gjh[4];
-        double o[2][4];
+        for (int h = 0; h < 4; ++h) {
+            int gjh[4];
+            double o[2][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
-        if (h < hmax) {
-            eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
-        } else {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
-        }
-#pragma unroll
-        for (int hh = 0; hh < 4; ++hh)
-            if (hh == h) {
+            for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
+            if (h < hmax) {
+                eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+            } else {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) out[r][4 * hh + c] = o[r][c];
+                    for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
             }
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh)
+                if (hh == h) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) out[r][4 * hh + c] = o[r][c];
+                }
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            int gjh[4];
+            double o[2][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
+            if (h < hmax) {
+                eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[r][4 * h + c] = o[r][c];
+        }
     }
 }
 

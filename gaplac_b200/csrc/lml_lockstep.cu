@@ -63,15 +63,15 @@ size_t lk_potrf_smem_bytes() { return sizeof(PotrfSmem); }
 // warps this kernel uses its own row map: warp w owns row block w (accumulator row 0, needs n-blocks 0..w) and row
 // block 7 - w (accumulator row 1, needs n-blocks 0..7-w): 9 blocks per warp.  The potrf kernel re-loads the tile in
 // the standard map, so nothing else sees this layout.
-template <int W>
+template <int W, int KCOLS>
 __device__ __forceinline__ void diag_mma(double (&acc)[2][NCC], const double *__restrict__ A, const TMap &tm) {
     const int sw = tm.t << 2;
     const double *pa0 = A + tm.t * TS + ((8 * W + tm.g) ^ sw);
     const double *pa1 = A + tm.t * TS + ((8 * (7 - W) + tm.g) ^ sw);
     const double *pbe = A + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);
     const double *pbo = A + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));
-#pragma unroll
-    for (int k = 0; k < 16; k += 4) {
+#pragma unroll 4
+    for (int k = 0; k < KCOLS; k += 4) {
         const double a0 = -pa0[k * TS], a1 = -pa1[k * TS];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
@@ -99,10 +99,11 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
     const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
     prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
 
-    const int Q = (TS / LKC) * j;
+    constexpr int DKC = 32, DCH = DKC * TS;  // only one operand is staged: two stages of 32 columns fill S
+    const int Q = (TS / DKC) * j;
     const double *srcA = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1) are contiguous
     auto issue = [&](int s) {
-        block_load_async<LCH * 8>(sm.S + (s & 1) * LCH, srcA + (size_t)s * LCH, tid);
+        block_load_async<DCH * 8>(sm.S + (s & 1) * DCH, srcA + (size_t)s * DCH, tid);
         cp_async_commit();
     };
     const bool z_in_smem = j * TS <= GPL_LK_ZMAX;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
     {
         int gi[2] = {j * TS + rows[0], j * TS + rows[1]};
         // quarters of 16 columns: row block 7 - w needs columns up to 63 - 8w
-        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, (63 - 8 * warp) / 16 + 1);
+        eval_block_acc<true, false>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, (63 - 8 * warp) / 16 + 1);
     }
     double ytmp = 0.0;
     if (tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
@@ -124,14 +125,14 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
         cp_async_wait<0>();
         __syncthreads();
         if (q + 1 < Q) issue(q + 1);
-        const double *a = sm.S + (q & 1) * LCH;
+        const double *a = sm.S + (q & 1) * DCH;
         switch (warp) {
-        case 0: diag_mma<0>(acc, a, tm); break;
-        case 1: diag_mma<1>(acc, a, tm); break;
-        case 2: diag_mma<2>(acc, a, tm); break;
-        default: diag_mma<3>(acc, a, tm); break;
+        case 0: diag_mma<0, DKC>(acc, a, tm); break;
+        case 1: diag_mma<1, DKC>(acc, a, tm); break;
+        case 2: diag_mma<2, DKC>(acc, a, tm); break;
+        default: diag_mma<3, DKC>(acc, a, tm); break;
         }
-        if (tid < TS) ytmp -= tile_row_dot(a, zsrc + q * LKC, tid, 0, LKC);
+        if (tid < TS) ytmp -= tile_row_dot(a, zsrc + q * DKC, tid, 0, DKC);
     }
     double *Tjj = wsL + tri_index(j, j) * TILE_ELEMS;
 #pragma unroll
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         int gi[2];
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
-        eval_block_acc<true>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc);
+        eval_block_acc<true, false>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc);
     }
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<0>();
