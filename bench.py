@@ -132,7 +132,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -183,13 +183,33 @@ def fp64_peak():
 
 
 def ncu_traffic():
-    p = os.path.join(ROOT, "profiles", "ncu_lml_summary.json")
+    """dram bytes per launch of the dominant kernel, from the committed ncu launch list (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
+
+
+def kernel_flops(n: int, B: int):
+    """Algorithmic FLOPs of one step split over the three kernels of the lockstep schedule:
+    n^3/3 = sum over 64x64 tile operations: potrf t^3/3 per diagonal tile, trsm t^3 and gemm 2 t^3 j per tile
+    below the diagonal of column j, syrk t^3 j per diagonal tile; the 2 n^2 of the covariance build and solve go
+    to the kernels in proportion to the tiles they generate."""
+    t, nt = 64.0, (n + 63) // 64
+    below_tiles = nt * (nt - 1) // 2
+    gemm = sum(j * (nt - 1 - j) for j in range(nt))
+    syrk = sum(range(nt))
+    ntri = nt * (nt + 1) // 2
+    total = algorithmic_flops(n)
+    tile3 = (n / nt) ** 3  # n need not be a multiple of 64: scale the tile cube so the parts sum to n^3/3
+    scale = (n ** 3 / 3.0) / (tile3 * (nt / 3.0 + below_tiles + 2 * gemm + syrk))
+    f_below = scale * tile3 * (below_tiles + 2 * gemm) + 2.0 * n * n * below_tiles / ntri
+    f_diag = scale * tile3 * syrk + 2.0 * n * n * nt / ntri
+    f_potrf = total - f_below - f_diag
+    return {"below": B * f_below, "diag": B * f_diag, "potrf": B * f_potrf}
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -258,7 +278,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     launches = ctx.launch_count() - l0
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop(t0, t1) if sampler else None
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     bad = int((dinfo != 0).sum().item())
@@ -266,6 +285,29 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, kern_ms = t.tolist()
+
+    # ---- per-kernel pass (untimed for `value`): CUDA events around every launch of the lockstep schedule ----------
+    import ctypes as C
+    lib = _lib.load()
+    lib.gpl_debug_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    ctx.set_option("profile_events", 1)
+    kms = np.zeros(3)
+    kl = np.zeros(3, dtype=np.int64)
+    reps = max(2, min(args.steps, 5))
+    for _ in range(reps):
+        flush.zero_()
+        ctx.lml_batched_dev(prog, n, d, dX.data_ptr(), False, dY.data_ptr(), y_batched, dTh.data_ptr(), p,
+                            dS2.data_ptr(), False, wl["jitter"], B, dlml.data_ptr(), 0, 0, dinfo.data_ptr(),
+                            stream.cuda_stream)
+        ms3 = (C.c_double * 3)()
+        l3 = (C.c_int * 3)()
+        lib.gpl_debug_last_timing(ctx.h, ms3, l3)
+        kms += np.array(list(ms3))
+        kl += np.array(list(l3))
+    ctx.set_option("profile_events", 0)
+    kms /= reps
+    kl //= reps
+    torch.cuda.synchronize()
 
     # ---- end-to-end arm: host buffers through gpl_lml_batched -----------------------------------------------
     hlml = None
@@ -294,6 +336,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e_ms = t.item()
+    clocks = sampler.stop(t0, time.perf_counter()) if sampler else None
     parity = float(np.max(np.abs(hlml - dlml.cpu().numpy()) / np.abs(hlml)))   # the two arms compute the same thing
     h2d = X.nbytes + Y.nbytes + Theta.nbytes + wl["sigma2"].nbytes
     d2h = B * 8 + B * 4
@@ -301,7 +344,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank == 0:
         peak, peak_src = fp64_peak()
         flops = B * algorithmic_flops(n)
-        ach = flops / (kern_ms * 1e-3) * 1e-12
+        step_ach = flops / (kern_ms * 1e-3) * 1e-12
+        kf = kernel_flops(n, B)
+        names = ["diag", "potrf", "below"]
+        dom = int(np.argmax(kms))            # dominant kernel by device time
+        dom_name = "lk_%s_kernel" % names[dom]
+        launches_dom = max(int(kl[dom]), 1)
+        ach = kf[names[dom]] / (kms[dom] * 1e-3) * 1e-12 if kms[dom] > 0 else 0.0
         out = {
             "metric": METRIC, "value": world * B / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -310,10 +359,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "sharding": f"independent proposals, {B} per rank, one NCCL all-gather of lml per step",
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed); per-CTA factor workspace "
                              "also exceeds L2", "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe on sm_100a)", "achieved": ach,
-                         "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu_traffic(),
-                         "peak_source": peak_src, "kernel": "lml_batched_kernel", "kernel_ms": kern_ms,
-                         "algorithmic_flops_per_launch": flops},
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA and DFMA share one pipe on sm_100a; tools/pipe_mix.cu)",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "kernel": dom_name,
+                         "kernel_launches_per_step": launches_dom,
+                         "kernel_avg_launch_ms": float(kms[dom]) / launches_dom,
+                         "kernel_share_of_step": float(kms[dom] / max(kms.sum(), 1e-12)),
+                         "algorithmic_flops_per_launch": kf[names[dom]] / launches_dom,
+                         "per_kernel_ms_per_step": {nm: float(v) for nm, v in zip(names, kms)},
+                         "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "ms": kern_ms,
+                                        "algorithmic_flops": flops}},
             "e2e": {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e_ms,
                     "api": "gpl_lml_batched (host buffers, blocking) via ctypes"},

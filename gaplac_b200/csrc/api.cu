@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/gaplac_b200.h"
 #include "kernels.h"
@@ -44,6 +45,9 @@ struct gpl_ctx {
     int chol_variant = 0;
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false;
     size_t lk_ws_limit = (size_t)12 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
+    int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
+    double lk_ms[3] = {0, 0, 0};            // last instrumented call: total ms in diag / potrf / below kernels
+    int lk_launches[3] = {0, 0, 0};
     // grow-only device buffers
     DevBuf lkTiles, lkD, lkZ, lkAcc;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
@@ -228,6 +232,16 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     pp.dblk = prm.dblk;
     pp.z = prm.z;
     pp.acc2 = ptr<double>(ctx->lkAcc);
+    std::vector<cudaEvent_t> evs;
+    std::vector<int> ev_kind;
+    auto mark = [&](int kind) {  // kind: 0 diag, 1 potrf, 2 below, -1 start
+        if (!ctx->profile_events) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+        ev_kind.push_back(kind);
+    };
     for (int off = 0; off < B; off += Bc) {
         const int nb = (B - off < Bc) ? B - off : Bc;
         prm.X = dX + (size_t)off * prm.x_stride;
@@ -236,19 +250,36 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
         prm.sigma2 = dsigma2 + (size_t)off * prm.sigma2_stride;
         pp.lml = dlml + off;
         pp.info = info_dev + off;
+        mark(-1);
         for (int j = 0; j < nt; ++j) {
             prm.j = j;
             pp.j = j;
             lk_diag_kernel<<<nb, NTHREADS, lk_step_smem_bytes(), st>>>(prm);
+            mark(0);
             lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);
+            mark(1);
             ctx->launches += 2;
             if (j + 1 < nt) {
                 lk_below_kernel<<<(unsigned)((size_t)nb * (nt - 1 - j)), NTHREADS, lk_step_smem_bytes(), st>>>(prm);
+                mark(2);
                 ctx->launches++;
             }
         }
     }
     CU(ctx, cudaGetLastError());
+    if (ctx->profile_events) {
+        CU(ctx, cudaStreamSynchronize(st));
+        for (int k = 0; k < 3; ++k) ctx->lk_ms[k] = 0.0, ctx->lk_launches[k] = 0;
+        for (size_t e = 1; e < evs.size(); ++e) {
+            if (ev_kind[e] >= 0) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, evs[e - 1], evs[e]);
+                ctx->lk_ms[ev_kind[e]] += ms;
+                ctx->lk_launches[ev_kind[e]]++;
+            }
+        }
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    }
     return GPL_OK;
 }
 
@@ -380,6 +411,7 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     if (!strcmp(key, "lml_variant")) ctx->lml_variant = value;
     else if (!strcmp(key, "chol_variant")) ctx->chol_variant = value;
     else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
+    else if (!strcmp(key, "profile_events")) ctx->profile_events = value;
     else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
     return GPL_OK;
 }
@@ -517,6 +549,14 @@ int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const doub
     if (dtheta && p > 0) CU(ctx, cudaMemcpyAsync(dtheta, ctx->bDtheta.p, (size_t)p * B * 8, cudaMemcpyDeviceToHost, st));
     if (dy) CU(ctx, cudaMemcpyAsync(dy, ctx->bDy.p, (size_t)n * B * 8, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+// Per-kernel device time of the last lockstep call made with option "profile_events" = 1: ms[0..2] = total time in the
+// diag / potrf / below kernels, launches[0..2] = their launch counts.  Not part of the public header (bench.py only).
+int gpl_debug_last_timing(gpl_ctx *ctx, double *ms, int *launches) {
+    if (!ctx || !ms || !launches) return GPL_ERR_ARG;
+    for (int k = 0; k < 3; ++k) ms[k] = ctx->lk_ms[k], launches[k] = ctx->lk_launches[k];
     return GPL_OK;
 }
 

@@ -1,5 +1,4 @@
-timeout 600 python tools/gpu_debug.py > gpurun_out/debug15.log 2>&1; grep -E "ERR|ok " gpurun_out/debug15.log | cut -c1-150 | grep -E "ERR|lml n|grad|c2|posterior n=700"
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8
-python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench15.json 2> gpurun_out/bench15.err; tail -2 gpurun_out/bench15.err
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench20.json 2> gpurun_out/bench20.err; tail -2 gpurun_out/bench20.err
 python -c "
-import json,sys; j=json.load(open('gpurun_out/bench15.json')); print('lockstep', round(j['value']), round(j['roofline']['frac'],4), j['arms_max_rel_diff'], j['not_pd_items'], j['gpu_launches'])"
+import json,sys; j=json.load(open('gpurun_out/bench20.json')); print(json.dumps({k:j[k] for k in ['value','ms_per_step','gpu_launches','clocks','cpu_baseline','e2e']},indent=0)); print(json.dumps(j['roofline'],indent=0))"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench20_ref.json; cut -c1-300 gpurun_out/bench20_ref.json
