@@ -38,6 +38,8 @@ struct gpl_ctx {
     int clock_khz = 0;
     char name[128] = {0};
     cudaStream_t stream = nullptr;
+    cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
+    DevBuf bigFlags;
     uint64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -289,7 +291,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     const size_t smem = big_smem_bytes();
     bool &attr_set = ctx->attr_big;
     if (!attr_set) {
-        CU(ctx, cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(ctx, cudaFuncSetAttribute(big_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(ctx, cudaFuncSetAttribute(big_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)big_trail_smem_bytes()));
@@ -303,26 +305,121 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     prm.info = dinfo;
     prm.y = y;
     prm.nt = nt;
-    for (int k0 = 0; k0 < nt; k0 += PANEL) {
-        const int j1 = (k0 + PANEL < nt) ? k0 + PANEL : nt;
+    prm.l0 = prm.l1 = 0;
+    prm.flags = nullptr;
+    const int NP = (nt + PANEL - 1) / PANEL;
+    auto cols_tiles = [&](int l0, int l1) {  // number of tiles (i, l), l0 <= l < l1, l <= i < nt
+        long long c = 0;
+        for (int l = l0; l < l1; ++l) c += nt - l;
+        return c;
+    };
+    auto factor_panel = [&](int P, cudaStream_t s, size_t diag_smem) {
+        const int k0 = P * PANEL, j1 = (k0 + PANEL < nt) ? k0 + PANEL : nt;
         prm.k0 = k0;
         prm.j1 = j1;
         for (int j = k0; j < j1; ++j) {
             prm.j = j;
-            big_diag_kernel<<<1, NTHREADS, smem, st>>>(prm);
+            big_diag_kernel<<<1, NTHREADS, diag_smem, s>>>(prm);
             ctx->launches++;
             if (j + 1 < nt) {
-                big_col_kernel<<<nt - j - 1, NTHREADS, smem, st>>>(prm);
+                big_col_kernel<<<nt - j - 1, NTHREADS, smem, s>>>(prm);
                 ctx->launches++;
             }
         }
-        if (j1 < nt) {
-            const long long ntrail = tri_index(nt - j1, 0);
-            big_trail_kernel<<<(unsigned)ntrail, NTHREADS, big_trail_smem_bytes(), st>>>(prm);
+    };
+    auto trail = [&](int P, int l0, int l1, cudaStream_t s) {  // update tile columns [l0, l1) with panel P
+        if (l0 >= l1) return;
+        prm.k0 = P * PANEL;
+        prm.j1 = prm.k0 + PANEL;
+        prm.l0 = l0;
+        prm.l1 = l1;
+        big_trail_kernel<<<(unsigned)cols_tiles(l0, l1), NTHREADS, big_trail_smem_bytes(), s>>>(prm);
+        ctx->launches++;
+    };
+    if (NP <= 2 || ctx->chol_variant == 2) {
+        // small problems: one stream, no look-ahead
+        for (int P = 0; P < NP; ++P) {
+            factor_panel(P, st, smem);
+            trail(P, (P + 1) * PANEL, nt, st);
+        }
+        CU(ctx, cudaGetLastError());
+        return GPL_OK;
+    }
+    // Look-ahead (depth 1).  A persistent worker CTA (big_worker_kernel, its own high-priority stream, a whole SM of
+    // shared memory) factors the diagonal tiles in turn; s_panel carries the column kernels (they spin on the worker's
+    // flag per column) and the update of the next panel's columns; s_trail carries the rest of the trailing update.
+    if (!ctx->s_panel) {
+        int lo = 0, hi = 0;
+        CU(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_worker, cudaStreamNonBlocking, hi));
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_panel, cudaStreamNonBlocking, hi));
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, lo));
+        CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
+    int rc = ensure(ctx, ctx->bigFlags, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int));
+    if (rc) return rc;
+    prm.flags = ptr<int>(ctx->bigFlags);
+    CU(ctx, cudaMemsetAsync(prm.flags, 0, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int), st));
+    const size_t diag_smem = 200 * 1024;
+    std::vector<cudaEvent_t> eF(NP), eB(NP);
+    for (int P = 0; P < NP; ++P) {
+        CU(ctx, cudaEventCreateWithFlags(&eF[P], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&eB[P], cudaEventDisableTiming));
+    }
+    cudaEvent_t e0, eW;
+    CU(ctx, cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&eW, cudaEventDisableTiming));
+    CU(ctx, cudaEventRecord(e0, st));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_panel, e0, 0));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_trail, e0, 0));
+    auto panel_cols = [&](int P) -> int {  // column kernels of panel P under the worker protocol
+        const int k0 = P * PANEL, j1 = (k0 + PANEL < nt) ? k0 + PANEL : nt;
+        prm.k0 = k0;
+        prm.j1 = j1;
+        CU(ctx, cudaMemsetAsync(prm.flags + P, 1, sizeof(int), ctx->s_panel));  // panel_ready[P]
+        for (int j = k0; j < j1 && j + 1 < nt; ++j) {
+            prm.j = j;
+            big_col_flag_kernel<<<nt - j - 1, NTHREADS, smem, ctx->s_panel>>>(prm);
             ctx->launches++;
         }
+        return (int)GPL_OK;
+    };
+    if (use_worker) {
+        CU(ctx, cudaStreamWaitEvent(ctx->s_worker, e0, 0));
+        big_worker_kernel<<<1, NTHREADS, diag_smem, ctx->s_worker>>>(prm);
+        ctx->launches++;
+        CU(ctx, cudaEventRecord(eW, ctx->s_worker));
+        if ((rc = panel_cols(0))) return rc;
+    } else {
+        factor_panel(0, ctx->s_panel, diag_smem);
     }
+    CU(ctx, cudaEventRecord(eF[0], ctx->s_panel));
+    for (int P = 0; P + 1 < NP; ++P) {
+        const int n0 = (P + 1) * PANEL, n1 = (n0 + PANEL < nt) ? n0 + PANEL : nt;  // columns of panel P + 1
+        if (P >= 1) CU(ctx, cudaStreamWaitEvent(ctx->s_panel, eB[P - 1], 0));
+        trail(P, n0, n1, ctx->s_panel);
+        if (use_worker) {
+            if ((rc = panel_cols(P + 1))) return rc;
+        } else {
+            factor_panel(P + 1, ctx->s_panel, diag_smem);
+        }
+        CU(ctx, cudaEventRecord(eF[P + 1], ctx->s_panel));
+        CU(ctx, cudaStreamWaitEvent(ctx->s_trail, eF[P], 0));
+        trail(P, n1, nt, ctx->s_trail);
+        CU(ctx, cudaEventRecord(eB[P], ctx->s_trail));
+    }
+    CU(ctx, cudaStreamWaitEvent(st, eF[NP - 1], 0));
+    CU(ctx, cudaStreamWaitEvent(st, eB[NP - 2], 0));
+    if (use_worker) CU(ctx, cudaStreamWaitEvent(st, eW, 0));
     CU(ctx, cudaGetLastError());
+    for (int P = 0; P < NP; ++P) {
+        cudaEventDestroy(eF[P]);
+        cudaEventDestroy(eB[P]);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(eW);
     return GPL_OK;
 }
 
@@ -394,11 +491,14 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    if (ctx->s_worker) cudaStreamDestroy(ctx->s_worker);
+    if (ctx->s_panel) cudaStreamDestroy(ctx->s_panel);
+    if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GPL_OK;

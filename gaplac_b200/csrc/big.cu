@@ -7,7 +7,8 @@
 // Two-level blocking (one CTA of 128 threads per tile, DMMA tile primitives of tile.cuh).  A panel is PANEL tile columns (256 matrix columns).  Inside a panel the tile columns are
 // factored left-looking (big_diag_kernel: 1 CTA; big_col_kernel: one CTA per tile below the diagonal); after
 // a panel, big_trail_kernel applies its rank-256 update to every remaining tile (one CTA per tile, K = 256 so
-// the trailing matrix moves through HBM once per panel, not once per tile column).
+// the trailing matrix moves through HBM once per panel, not once per tile column).  The host overlaps the (serial,
+// latency-bound) factorisation of panel P+1 with the trailing update of panel P on two streams (look-ahead, api.cu).
 #include "kernels.h"
 #include "tile.cuh"
 
@@ -148,6 +149,121 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
     }
 }
 
+// ---- look-ahead protocol -----------------------------------------------------------------------------------------
+// The diagonal tiles are the serial chain of the factorisation.  With look-ahead they are factored by ONE persistent CTA
+// (big_worker_kernel) that owns a whole SM for the duration (200 KiB of dynamic shared memory: no DMMA-streaming CTA can
+// share its sub-partitions and starve its pivot chains, tools/pipe_mix.cu), while the host streams the column and
+// trailing kernels around it.  Synchronisation is through three flag arrays in global memory:
+//   panel_ready[P]  set by the host (stream-ordered memset) once every earlier panel's update of panel P's columns is done
+//   rowdone[i]      = j + 1 once tile (i, j) is final and y_i carries column j   (written by big_col_flag_kernel)
+//   diagdone[j]     != 0 once L_jj, W_jj and z_j are stored                      (written by the worker)
+__device__ __forceinline__ int ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void wait_flag_ge(const int *p, int v, int tid) {
+    if (tid == 0) {
+        while (ld_flag(p) < v) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, nt = prm.nt;
+    const TMap tm = thread_map(tid);
+    int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
+    constexpr int PANEL_ = 4;
+    for (int j = 0; j < nt; ++j) {
+        const int k0 = (j / PANEL_) * PANEL_;
+        if (j == k0) wait_flag_ge(panel_ready + j / PANEL_, 1, tid);
+        if (j > 0) wait_flag_ge(rowdone + j, j, tid);
+        double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
+        __syncthreads();
+        tile_load_async(sm.A, Tjj, tid);
+        if (j > k0) tile_load_async(sm.Bt, prm.tiles + tri_index(j, k0) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double acc[2][NCC];
+        acc_from_tile(acc, sm.A, tm);
+        for (int k = k0; k < j; ++k) {  // in-panel left-looking update; tile k sits in Bt / A alternately
+            double *cur = ((k - k0) & 1) ? sm.A : sm.Bt;
+            double *nxt = ((k - k0) & 1) ? sm.Bt : sm.A;
+            __syncthreads();  // everyone done reading `nxt` (previous step / accumulator load)
+            if (k + 1 < j) {
+                tile_load_async(nxt, prm.tiles + tri_index(j, k + 1) * TILE_ELEMS, tid);
+                cp_async_commit();
+            }
+            tile_mma<true>(acc, cur, cur, tm, 0, TS);
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+        if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
+        acc_to_tile(Tjj, acc, tm);
+        __syncthreads();
+        acc_to_tile(sm.A, acc, tm);
+        if (prm.y && tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+        __syncthreads();
+        double e[2][NCC];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+        tile_trsm_ld(e, sm.A, sm.D, tm);
+        acc_to_tile_t(sm.W, e, tm);
+        __syncthreads();
+        tile_store(prm.winv + (size_t)j * TILE_ELEMS, sm.W, tid);
+        if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
+        if (prm.y && tid < TS) prm.y[j * TS + tid] = tile_row_dot(sm.W, sm.ybuf, tid, 0, tid + 1);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
+    const TMap tm = thread_map(tid);
+    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
+    double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
+    // the tile itself receives no further outside update: fetch it while the worker is still on the diagonal tile
+    tile_load_async(sm.A, Tij, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][NCC];
+    acc_from_tile(acc, sm.A, tm);
+    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, W_jj, z_j stored; tiles (j, k0..j-1) were final before that
+    tile_load_async(sm.W, prm.winv + (size_t)j * TILE_ELEMS, tid);
+    cp_async_commit();
+    for (int k = prm.k0; k < j; ++k) {
+        __syncthreads();
+        tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+        tile_load_async(sm.Bt, prm.tiles + tri_index(j, k) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    tile_trsm_w(acc, sm.W, tm);
+    acc_to_tile(Tij, acc, tm);
+    if (prm.y) {
+        __syncthreads();
+        acc_to_tile(sm.A, acc, tm);
+        if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+        __syncthreads();
+        if (tid < TS) prm.y[i * TS + tid] = __ldcg(prm.y + i * TS + tid) - tile_row_dot(sm.A, sm.ybuf, tid, 0, TS);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int *>(rowdone + i) = j + 1;
+}
+
 // trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'
 __global__ void __launch_bounds__(NTHREADS, 4) big_trail_kernel(BigParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -155,9 +271,13 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_trail_kernel(BigParams prm) {
     constexpr int KC = 16, CH = KC * TS;
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
-    int ii, ll;
-    tri_unrank(blockIdx.x, ii, ll);
-    const int i = prm.j1 + ii, l = prm.j1 + ll;
+    // linear block index -> tile (i, l), l0 <= l < l1, l <= i < nt (column by column)
+    int idx = blockIdx.x, l = prm.l0;
+    while (idx >= prm.nt - l) {
+        idx -= prm.nt - l;
+        ++l;
+    }
+    const int i = l + idx;
     const bool diag = (i == l);
     double *Til = prm.tiles + tri_index(i, l) * TILE_ELEMS;
     const int Q = (TS / KC) * (prm.j1 - prm.k0);  // the panel's tiles of a tile row are contiguous

@@ -93,10 +93,16 @@ struct BigParams {
     int j;          // current tile column
     int k0;         // first tile column of the current panel (left-looking inside the panel)
     int j1;         // trailing update: one past the last tile column of the finished panel
+    int l0, l1;     // trailing update: tile columns [l0, l1) are updated by this launch (all rows i >= l)
+    int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] (device ints)
 };
+constexpr int BIG_MAXP = 64;  // panels the flag block has room for
 __global__ void big_diag_kernel(BigParams prm);   // 1 CTA
 __global__ void big_col_kernel(BigParams prm);    // nt - j - 1 CTAs
-__global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l >= j1)
+__global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l, l0 <= l < l1)
+// look-ahead protocol: one persistent CTA factors every diagonal tile in turn; the column kernel waits for it per column
+__global__ void big_worker_kernel(BigParams prm);    // 1 CTA for the whole factorisation (owns an SM)
+__global__ void big_col_flag_kernel(BigParams prm);  // nt - j - 1 CTAs; spins on diagdone[j], publishes rowdone[i]
 size_t big_smem_bytes();
 size_t big_trail_smem_bytes();
 
