@@ -20,7 +20,7 @@ using namespace gpl;
 namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
-constexpr int PANEL = 4;        // tile columns per panel of the large-n factorisation
+constexpr int PANEL = BIG_PANEL;  // tile columns per panel of the large-n factorisation (kernels.h)
 constexpr int SMALL_MAX_N = 512;  // posterior fits up to this n run on the one-CTA fused kernel
 
 thread_local std::string g_last_error;
@@ -990,9 +990,16 @@ int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     cp.theta = ptr<double>(ctx->bTheta);
     cp.diag_add = sigma2 + jitter;
     cp.tiles = tiles;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (ctx->profile_events) {
+        for (auto &e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+    }
     cov_tiles_kernel<<<(unsigned)ntri, NTHREADS, 0, st>>>(cp);
     ctx->launches++;
+    if (ctx->profile_events) cudaEventRecord(ev[1], st);
     if ((rc = big_factor(ctx, tiles, winv, pivlog, dinfo, ptr<double>(ctx->bY), nt, st))) return rc;
+    if (ctx->profile_events) cudaEventRecord(ev[2], st);
     big_reduce_kernel<<<1, NTHREADS, 0, st>>>(pivlog, ptr<double>(ctx->bY), nt * TS, dres);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
@@ -1001,6 +1008,15 @@ int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     CU(ctx, cudaMemcpyAsync(h_res, dres, 16, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaMemcpyAsync(&h_info, dinfo, 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
+    if (ctx->profile_events) {  // lk_ms[0] = covariance build, lk_ms[1] = factorisation + forward solve (device time)
+        float a_ms = 0.f, b_ms = 0.f;
+        cudaEventElapsedTime(&a_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&b_ms, ev[1], ev[2]);
+        ctx->lk_ms[0] = a_ms;
+        ctx->lk_ms[1] = b_ms;
+        ctx->lk_ms[2] = 0.0;
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     if (info) *info = h_info;
     if (logdet) *logdet = h_info ? NAN : h_res[0];
     *lml = h_info ? -INFINITY : -0.5 * ((double)n * LOG2PI + h_res[0] + h_res[1]);

@@ -9,6 +9,8 @@
 // a panel, big_trail_kernel applies its rank-256 update to every remaining tile (one CTA per tile, K = 256 so
 // the trailing matrix moves through HBM once per panel, not once per tile column).  The host overlaps the (serial,
 // latency-bound) factorisation of panel P+1 with the trailing update of panel P on two streams (look-ahead, api.cu).
+#include <cstdio>
+
 #include "kernels.h"
 #include "tile.cuh"
 
@@ -172,11 +174,24 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
     const int tid = threadIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
     int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
-    constexpr int PANEL_ = 4;
+    constexpr int PANEL_ = BIG_PANEL;
+#ifdef GPL_BIG_PROFILE
+    long long t_wait_panel = 0, t_wait_row = 0, t_begin = clock64();
+#endif
     for (int j = 0; j < nt; ++j) {
         const int k0 = (j / PANEL_) * PANEL_;
+#ifdef GPL_BIG_PROFILE
+        long long ta = clock64();
+#endif
         if (j == k0) wait_flag_ge(panel_ready + j / PANEL_, 1, tid);
+#ifdef GPL_BIG_PROFILE
+        long long tb = clock64();
+        t_wait_panel += tb - ta;
+#endif
         if (j > 0) wait_flag_ge(rowdone + j, j, tid);
+#ifdef GPL_BIG_PROFILE
+        t_wait_row += clock64() - tb;
+#endif
         double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
         __syncthreads();
         tile_load_async(sm.A, Tjj, tid);
@@ -220,6 +235,9 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         __syncthreads();
         if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;
     }
+#ifdef GPL_BIG_PROFILE
+    if (tid == 0) printf("worker: total %lld clk, waiting for panel_ready %lld, for rowdone %lld, working %lld\n", clock64() - t_begin, t_wait_panel, t_wait_row, clock64() - t_begin - t_wait_panel - t_wait_row);
+#endif
 }
 
 __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {

@@ -97,6 +97,10 @@ struct BigParams {
     int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] (device ints)
 };
 constexpr int BIG_MAXP = 64;  // panels the flag block has room for
+#ifndef GPL_BIG_PANEL
+#define GPL_BIG_PANEL 4
+#endif
+constexpr int BIG_PANEL = GPL_BIG_PANEL;  // tile columns per panel of the large-n factorisation
 __global__ void big_diag_kernel(BigParams prm);   // 1 CTA
 __global__ void big_col_kernel(BigParams prm);    // nt - j - 1 CTAs
 __global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l, l0 <= l < l1)

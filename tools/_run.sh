@@ -1,3 +1,1 @@
-timeout 120 python tools/run_c5.py 1500 2 2>&1 | tail -2
-timeout 120 python tools/run_c5.py 8192 4 2>&1 | tail -3
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+for v in "" _p8 _p2; do echo "variant $v"; GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so timeout 120 python tools/run_c5.py 8192 3 2>&1 | tail -1; done
