@@ -198,6 +198,8 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
         CU(ctx, cudaFuncSetAttribute(lk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_below_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_potrf_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_potrf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)lk_potrf_warp_smem_bytes()));
         ctx->attr_lk = true;
     }
     const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16;
@@ -258,7 +260,13 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
             pp.j = j;
             lk_diag_kernel<<<nb, NTHREADS, lk_step_smem_bytes(), st>>>(prm);
             mark(0);
-            lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);
+            pp.B = nb;
+            if (ctx->lml_variant == 2) {
+                lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);  // one CTA per item (A/B reference)
+            } else {
+                const int ipc = lk_potrf_warp_items_per_cta();
+                lk_potrf_warp_kernel<<<(nb + ipc - 1) / ipc, 32 * ipc, lk_potrf_warp_smem_bytes(), st>>>(pp);
+            }
             mark(1);
             ctx->launches += 2;
             if (j + 1 < nt) {

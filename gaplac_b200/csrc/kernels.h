@@ -43,7 +43,7 @@ struct LkParams {
     double *z;      // B x nt*64: right-hand side / z = L^-1 y
 };
 struct LkPotrfParams {
-    int n, nt, j;
+    int n, nt, j, B;
     double *tiles, *dblk, *z;
     double *acc2;  // B x 2: running z'z and logdet
     double *lml;
@@ -54,6 +54,9 @@ __global__ void lk_potrf_kernel(const __grid_constant__ LkPotrfParams prm);  // 
 __global__ void lk_below_kernel(const __grid_constant__ LkParams prm);       // grid B * (nt - 1 - j)
 size_t lk_step_smem_bytes();
 size_t lk_potrf_smem_bytes();
+__global__ void lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm);  // one warp per item
+size_t lk_potrf_warp_smem_bytes();
+int lk_potrf_warp_items_per_cta();
 
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
 struct CovParams {

@@ -190,6 +190,199 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_potrf_kernel(const __grid_cons
     }
 }
 
+// ---- Cholesky of the diagonal tiles of column j, one WARP per GP ----------------------------------------------------------
+// The factorisation of a 64 x 64 tile is a chain of 64 dependent pivots; with one CTA per tile three of four warps sat
+// at barriers while the chain warp ran, and a tile took ~59 k clocks (ncu: 45 % of warp time in the barrier after the
+// chain).  Here every warp owns one GP's tile in shared memory and runs the whole blocked algorithm by itself
+// (__syncwarp only): five independent chains per SM, no idle warps.  Per 16-column panel: the 16 x 16 diagonal block
+// is factored in registers (one row per lane, warp shuffles), inverted by forward substitution, the rows below are
+// solved against it in place, the right-hand side is advanced (z = L^-1 y), and the trailing lower blocks take their
+// rank-16 update through DMMA with accumulators loaded from / stored to the shared tile.
+constexpr int PW_WARPS = 6;
+struct __align__(16) PotrfWarpSmem {
+    double T[TILE_ELEMS];
+    double W16[DBLK];
+    double y[TS];
+    double piv[TS];
+    double rs[16];
+};
+size_t lk_potrf_warp_smem_bytes() { return sizeof(PotrfWarpSmem) * PW_WARPS; }
+int lk_potrf_warp_items_per_cta() { return PW_WARPS; }
+
+__global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * PW_WARPS + warp;
+    if (b >= prm.B) return;  // whole warp
+    PotrfWarpSmem &sm = reinterpret_cast<PotrfWarpSmem *>(smem_raw)[warp];
+    const int nt = prm.nt, j = prm.j, g = lane >> 2, t = lane & 3;
+    const long long ntri = tri_index(nt, 0);
+    double *Tjj = prm.tiles + ((size_t)b * ntri + tri_index(j, j)) * TILE_ELEMS;
+    double *zb = prm.z + (size_t)b * nt * TS;
+    double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
+#pragma unroll 8
+    for (int it = 0; it < TILE_BYTES / 16 / 32; ++it) {
+        const int idx = it * 32 + lane;
+        cp_async16(reinterpret_cast<char *>(sm.T) + idx * 16, reinterpret_cast<const char *>(Tjj) + idx * 16);
+    }
+    cp_async_commit();
+    sm.y[lane] = zb[j * TS + lane];
+    sm.y[lane + 32] = zb[j * TS + lane + 32];
+    cp_async_wait<0>();
+    __syncwarp();
+    int fail = -1;
+    const int r_own = lane & 15;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        // 16 x 16 diagonal block: one row per lane (lanes 16..31 mirror), pivots and columns through shuffles
+        double a[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] = sm.T[tidx(16 * p + r_own, 16 * p + c)];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            double piv = __shfl_sync(0xffffffffu, a[c], c);
+            if (!(piv > 0.0)) {
+                if (fail < 0) fail = 16 * p + c;
+                piv = 1.0;
+            }
+            const double rs = rsqrt(piv);
+            if (lane == 0) {
+                sm.piv[16 * p + c] = piv;
+                sm.rs[c] = rs;
+            }
+            const double l = a[c] * rs;
+            a[c] = (r_own >= c) ? l : 0.0;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 16; ++c2) {
+                const double l2 = __shfl_sync(0xffffffffu, l, c2);
+                a[c2] = fma(-l, l2, a[c2]);
+            }
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                sm.T[tidx(16 * p + r_own, 16 * p + c)] = a[c];
+            }
+        }
+        __syncwarp();
+        {
+            double x[16];  // column r_own of L16^-1 (axpy-form forward substitution)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = (i == r_own) ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                x[c] *= sm.rs[c];
+#pragma unroll
+                for (int i = c + 1; i < 16; ++i) x[i] = fma(-sm.T[tidx(16 * p + i, 16 * p + c)], x[c], x[i]);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sm.W16[i * DLD + r_own] = x[i];
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < DBLK; e += 32) Dg[p * DBLK + e] = sm.W16[e];
+        // rows below the block: L[r, panel] = T[r, panel] * W16'   (in place, one row per lane, two passes)
+        for (int r = 16 * (p + 1) + lane; r < TS; r += 32) {
+            double pk[16], out[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk[k] = sm.T[tidx(r, 16 * p + k)];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 <= c / 2; ++k2) {  // W16 row c is zero beyond column c
+                    const double2 w = *reinterpret_cast<const double2 *>(&sm.W16[c * DLD + 2 * k2]);
+                    s0 = fma(pk[2 * k2], w.x, s0);
+                    s1 = fma(pk[2 * k2 + 1], w.y, s1);
+                }
+                out[c] = s0 + s1;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sm.T[tidx(r, 16 * p + c)] = out[c];
+        }
+        // right-hand side: z_p = W16 y_p, then y_below -= L[below, panel] z_p
+        double zp = 0.0;
+        {
+            double z1 = 0.0;  // W16 row is zero beyond the diagonal: no triangular predicate needed
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const double2 w = *reinterpret_cast<const double2 *>(&sm.W16[r_own * DLD + 2 * k2]);
+                const double2 yv = *reinterpret_cast<const double2 *>(&sm.y[16 * p + 2 * k2]);
+                zp = fma(w.x, yv.x, zp);
+                z1 = fma(w.y, yv.y, z1);
+            }
+            zp += z1;
+        }
+        __syncwarp();
+        if (lane < 16) sm.y[16 * p + lane] = zp;
+        __syncwarp();
+        for (int r = 16 * (p + 1) + lane; r < TS; r += 32) {
+            double s = sm.y[r];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s = fma(-sm.T[tidx(r, 16 * p + k)], sm.y[16 * p + k], s);
+            sm.y[r] = s;
+        }
+        // trailing lower blocks (8 x 8): T[rb, cb] -= L[rb, panel] L[cb, panel]'
+        for (int rb = 2 * (p + 1); rb < 8; ++rb) {
+            const int cb0 = 2 * (p + 1);
+            double av[4], cv[6][2], bv[6][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) av[kk] = -sm.T[tidx(8 * rb + g, 16 * p + 4 * kk + t)];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                if (cb0 + q <= rb) {
+                    const int cb = cb0 + q;
+                    cv[q][0] = sm.T[tidx(8 * rb + g, 8 * cb + 2 * t)];
+                    cv[q][1] = sm.T[tidx(8 * rb + g, 8 * cb + 2 * t + 1)];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) bv[q][kk] = sm.T[tidx(8 * cb + g, 16 * p + 4 * kk + t)];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                    if (cb0 + q <= rb) dmma884(cv[q][0], cv[q][1], av[kk], bv[q][kk]);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                if (cb0 + q <= rb) {
+                    const int cb = cb0 + q;
+                    sm.T[tidx(8 * rb + g, 8 * cb + 2 * t)] = cv[q][0];
+                    sm.T[tidx(8 * rb + g, 8 * cb + 2 * t + 1)] = cv[q][1];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // results: L_jj in place, z_j, running z'z and logdet, failure report, lml after the last column
+#pragma unroll 8
+    for (int it = 0; it < TILE_BYTES / 16 / 32; ++it) {
+        const int idx = it * 32 + lane;
+        reinterpret_cast<double2 *>(Tjj)[idx] = reinterpret_cast<const double2 *>(sm.T)[idx];
+    }
+    const double z0 = sm.y[lane], z1 = sm.y[lane + 32];
+    zb[j * TS + lane] = z0;
+    zb[j * TS + lane + 32] = z1;
+    double zq = fma(z0, z0, z1 * z1), lg = log(sm.piv[lane]) + log(sm.piv[lane + 32]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        zq += __shfl_xor_sync(0xffffffffu, zq, o);
+        lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    }
+    if (lane == 0) {
+        int inf = prm.info[b];
+        if (fail >= 0 && inf == 0) {
+            inf = j * TS + fail + 1;
+            prm.info[b] = inf;
+        }
+        const double q = (j ? prm.acc2[2 * b] : 0.0) + zq, l = (j ? prm.acc2[2 * b + 1] : 0.0) + lg;
+        prm.acc2[2 * b] = q;
+        prm.acc2[2 * b + 1] = l;
+        if (j == nt - 1) prm.lml[b] = inf ? -INFINITY : -0.5 * ((double)prm.n * LOG2PI + l + q);
+    }
+}
+
 // ---- tiles below the diagonal of column j -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_constant__ LkParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

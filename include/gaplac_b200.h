@@ -87,7 +87,7 @@ int gpl_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
- * per-item kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap) */
+ * per-item kernel, 2 lockstep with the one-CTA-per-item potrf kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);
 /* device facts for reports: name (<= len bytes), SM count, SM clock kHz */
 int gpl_device_info(gpl_ctx *ctx, char *name, int len, int *sm_count, int *clock_khz);

@@ -1,1 +1,4 @@
-for v in "" _p8 _p2; do echo "variant $v"; GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so timeout 120 python tools/run_c5.py 8192 3 2>&1 | tail -1; done
+set -x
+timeout 300 python bench.py --steps 2 --warmup 1 > gpurun_out/b.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_potrf_warp -s 20 -c 2 -o gpurun_out/pw -f python bench.py --steps 2 --warmup 1 > gpurun_out/ncu.log 2>&1
+ls -la gpurun_out/pw.ncu-rep
