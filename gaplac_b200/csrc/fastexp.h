@@ -86,17 +86,23 @@ GPL_HD double fast_exp(double x, const double *__restrict__ tab) {
 // version's per-call branch kept them serial, which left the covariance tiles latency-bound: profiles/ README).
 template <int N>
 GPL_HD void fast_exp_vec(double (&x)[N], const double *__restrict__ tab) {
-    double mx = 0.0;
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) ok = ok && (fabs(x[i]) <= 700.0);  // false for NaN
-    (void)mx;
     if (ok) {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = fast_exp_core(x[i], tab);
     } else {
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) x[i] = fast_exp(x[i], tab);
+        // rare (deep underflow / NaN somewhere in the group): the general exp for every entry.  Unrolled with static
+        // indices so that x[] stays in registers (a rolled loop here put the whole array in local memory).
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#ifdef __CUDA_ARCH__
+            x[i] = exp_general(x[i]);
+#else
+            x[i] = exp(x[i]);
+#endif
+        }
     }
 }
 

@@ -95,25 +95,32 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
         for (int c = 0; c < C; ++c) out[r][c] = 0.0;
 
     for (int t = 0; t < P.n_terms; ++t) {
+        if (!SAME && ((P.has_noise >> t) & 1)) continue;  // Noise terms vanish on cross-covariances
         double prod[R][C];
         const double coef = P.coef[t];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) prod[r][c] = coef;
+        bool fresh = true;  // prod not materialised yet: the first factor writes coef * k instead of multiplying
         for (int f = P.term_begin[t]; f < P.term_begin[t + 1]; ++f) {
             const int kind = P.f[f].kind;
             const double a = S.a[f];
             if (kind == F_PARAM) {
+                if (fresh) {
+                    const double ca = coef * a;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                    for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) prod[r][c] *= a;
+                        for (int c = 0; c < C; ++c) prod[r][c] = ca;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) prod[r][c] *= a;
+                }
             } else if (kind == F_NOISE) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) prod[r][c] = (SAME && gi[r] == gj[c]) ? prod[r][c] : 0.0;
+                    for (int c = 0; c < C; ++c)
+                        prod[r][c] = (SAME && gi[r] == gj[c]) ? (fresh ? coef : prod[r][c]) : 0.0;
             } else {
                 const int col = P.f[f].col;
                 double xi[R], xj[C];
@@ -123,48 +130,75 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
                 for (int c = 0; c < C; ++c) xj[c] = Xb[(size_t)col * ldb + cj[c]];
                 if (kind == F_SQEXP || kind == F_OU) {
                     double e[R * C];
+                    if (kind == F_SQEXP) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
+                        for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const double d = xi[r] - xj[c];
-                            e[r * C + c] = a * (kind == F_SQEXP ? d * d : fabs(d));
-                        }
+                            for (int c = 0; c < C; ++c) {
+                                const double d = xi[r] - xj[c];
+                                e[r * C + c] = a * (d * d);
+                            }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int c = 0; c < C; ++c) e[r * C + c] = a * fabs(xi[r] - xj[c]);
+                    }
                     fast_exp_vec<R * C>(e, S.etab);
+                    if (fresh) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
+                        for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] *= e[r * C + c];
+                            for (int c = 0; c < C; ++c) prod[r][c] = coef * e[r * C + c];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int c = 0; c < C; ++c) prod[r][c] *= e[r * C + c];
+                    }
                 } else if (kind == F_LINEAR) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] *= fma(xi[r], xj[c], a);
+                        for (int c = 0; c < C; ++c)
+                            prod[r][c] = (fresh ? coef : prod[r][c]) * fma(xi[r], xj[c], a);
                 } else {  // F_CAT
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] = (xi[r] == xj[c]) ? prod[r][c] : 0.0;
+                        for (int c = 0; c < C; ++c) prod[r][c] = (xi[r] == xj[c]) ? (fresh ? coef : prod[r][c]) : 0.0;
                 }
             }
+            fresh = false;
         }
+        if (fresh) {  // a term without factors: the bare coefficient
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) out[r][c] += coef;
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) out[r][c] += prod[r][c];
+        }
+    }
+    if (SAME) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int c = 0; c < C; ++c) out[r][c] += prod[r][c];
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const bool inr = gi[r] < na && gj[c] < nb;
-            if (SAME) {
+            for (int c = 0; c < C; ++c) {
+                const bool inr = gi[r] < na && gj[c] < nb;
                 if (gi[r] == gj[c]) out[r][c] = inr ? out[r][c] + diag_add : 1.0;
                 else if (!inr) out[r][c] = 0.0;
-            } else if (!inr) {
-                out[r][c] = 0.0;
             }
-        }
+    } else if (gi[R - 1] >= na || gj[C - 1] >= nb) {  // indices ascend within a block: only edge blocks need masking
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (gi[r] >= na || gj[c] >= nb) out[r][c] = 0.0;
+    }
 }
 
 // The 2 x 16 accumulator block of one thread (tile.cuh: rows gi[0..1], columns cbase + 8 (cc/2) + 2 t + cc%2) as four

@@ -149,7 +149,7 @@ int compile_program(const gpl_op *ops, int n_ops, DevProgram *out, char *msg) {
                 snprintf(msg, 160, "kernel-program: more than %d factors after expansion", GPL_MAX_FACTORS);
                 return GPL_ERR_LIMIT;
             }
-            if (f.kind == F_NOISE) out->has_noise = 1;
+            if (f.kind == F_NOISE) out->has_noise |= 1 << t;
             out->f[nf++] = f;
         }
     }

@@ -1,4 +1,6 @@
 set -x
-timeout 300 python bench.py --steps 2 --warmup 1 > gpurun_out/b.log 2>&1 || exit 1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_potrf_warp -s 20 -c 2 -o gpurun_out/pw -f python bench.py --steps 2 --warmup 1 > gpurun_out/ncu.log 2>&1
-ls -la gpurun_out/pw.ncu-rep
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_pw.json
+python - <<'PY'
+import json; d=json.load(open('gpurun_out/bench_pw.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['per_kernel_ms_per_step'])
+PY
