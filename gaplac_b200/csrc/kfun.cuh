@@ -259,6 +259,52 @@ __device__ __forceinline__ void eval_block_acc(const DevProgram &P, const ItemSc
     }
 }
 
+// Same result as eval_block_acc, built for the throughput kernels: the quarters run through ONE rolled copy of the
+// evaluation code per pass (the four unrolled copies made a 38 KB loop body that the instruction cache could not hold:
+// 20 % of the j = 0 launch stalled on instruction fetch), and each quarter parks its 8 values in a thread-private
+// column of a shared-memory slot (NTHREADS x 8 doubles = 8 KiB, conflict-free, no barrier needed) from where they are
+// read back into statically indexed accumulator registers.  NSLOT slots -> 4 / NSLOT passes.
+template <bool SAME, int NSLOT>
+__device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const ItemScalars &S,
+                                                   const double *__restrict__ Xa, int lda, int na, const int (&gi)[2],
+                                                   const double *__restrict__ Xb, int ldb, int nb, int cbase, int t,
+                                                   double diag_add, double *const (&slot)[NSLOT], int tid,
+                                                   double (&out)[2][16], int hmax = 4) {
+    static_assert(NSLOT == 1 || NSLOT == 2 || NSLOT == 4, "slots");
+#pragma unroll
+    for (int pass = 0; pass < 4 / NSLOT; ++pass) {
+#pragma unroll 1
+        for (int hh = 0; hh < NSLOT; ++hh) {
+            const int h = pass * NSLOT + hh;
+            int gjh[4];
+            double o[2][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
+            if (h < hmax) {
+                eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
+            }
+            double *dst = slot[0];
+#pragma unroll
+            for (int q = 1; q < NSLOT; ++q) dst = (hh == q) ? slot[q] : dst;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dst[(r * 4 + c) * 128 + tid] = o[r][c];
+        }
+#pragma unroll
+        for (int hh = 0; hh < NSLOT; ++hh)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[r][4 * (pass * NSLOT + hh) + c] = slot[hh][(r * 4 + c) * 128 + tid];
+    }
+}
+
 // Contract a weight block w[r][c] with dK/dtheta_s for every slot s:  g[s] += sum_rc w[r][c] dK[r][c]/dtheta_s.
 // gsum: shared-memory accumulators (GPL_MAX_THETA doubles); one atomicAdd per (term, factor-with-slot, warp).
 template <int R, int C>

@@ -110,14 +110,25 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
     if (z_in_smem)
         for (int t = tid; t < j * TS; t += NTHREADS) sm.zs[t] = zb[t];
     const double *zsrc = z_in_smem ? sm.zs : zb;
-    if (Q > 0) issue(0);
+    if (GPL_LK_NSLOT == 2 && Q > 0) issue(0);
     __syncthreads();  // item scalars, z
     const int rows[2] = {8 * warp + tm.g, 8 * (7 - warp) + tm.g};  // this kernel's row map
     double acc[2][NCC];
     {
         int gi[2] = {j * TS + rows[0], j * TS + rows[1]};
         // quarters of 16 columns: row block 7 - w needs columns up to 63 - 8w
-        eval_block_acc<true, false>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, acc, (63 - 8 * warp) / 16 + 1);
+        // stage 0 of the update operands is in flight into the first half of S; the second half parks the quarters
+#if GPL_LK_NSLOT == 2
+        double *const slot[2] = {sm.S + 2 * LCH, sm.S + 3 * LCH};
+#else
+        double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
+#endif
+        eval_block_acc_scr<true, GPL_LK_NSLOT>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, slot, tid, acc,
+                                               (63 - 8 * warp) / 16 + 1);
+        if (GPL_LK_NSLOT == 4) {
+            __syncthreads();  // every thread has read its quarters back
+            if (Q > 0) issue(0);
+        }
     }
     double ytmp = 0.0;
     if (tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
@@ -396,7 +407,6 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     const long long ntri = tri_index(nt, 0);
     double *wsL = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
     const double *X = item_ptr(prm.X, prm.x_stride, b);
-    const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
     {  // pull this tile's inputs into L1 before the covariance code asks for them (its first loads stalled ~9 % of the
        // j = 0 launch on L2 round trips: profiles/ README)
         const int row = (tid < TS ? i : j) * TS + (tid & (TS - 1));
@@ -429,8 +439,12 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         static_assert(DSIZE * 8 % (16 * NTHREADS) == 0, "D in whole 16-byte chunks per thread");
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
     }
-    if (Q > 0) issue(0);
-    else issue_l01();
+    if (GPL_LK_NSLOT == 2) {
+        if (Q > 0) issue(0);
+        else issue_l01();
+    } else {
+        cp_async_commit();
+    }
     __syncthreads();  // item scalars
     double acc[2][NCC];
     {
@@ -439,7 +453,17 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
-        eval_block_acc<false, false>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, acc);
+#if GPL_LK_NSLOT == 2
+        double *const slot[2] = {sm.S + LCH, sm.S + 3 * LCH};  // A1 / B1: not written before update step 1 is issued
+#else
+        double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
+#endif
+        eval_block_acc_scr<false, GPL_LK_NSLOT>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
+        if (GPL_LK_NSLOT == 4) {
+            __syncthreads();
+            if (Q > 0) issue(0);
+            else issue_l01();
+        }
     }
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<0>();
