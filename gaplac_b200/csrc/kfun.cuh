@@ -14,6 +14,7 @@ namespace gpl {
 struct ItemScalars {
     double a[GPL_MAX_FACTORS];   // SQEXP: -1/(2 l^2); OU: -1/l; LINEAR: c; PARAM: theta
     double da[GPL_MAX_FACTORS];  // derivative scale: SQEXP 1/l^3 (dk = k d^2 / l^3); OU 1/l^2 (dk = k |d| / l^2)
+    double tc[GPL_MAX_TERMS];    // per term: coef * prod of its F_PARAM factors
     double etab[64];             // 2^(j/64) for fast_exp (fastexp.h), copied from constant memory once per CTA
 };
 
@@ -36,6 +37,12 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
         S->da[tid] = da;
     }
     if (tid >= 64 && tid < 128) S->etab[tid - 64] = c_exptab[tid - 64];
+    if (tid >= 32 && tid < 32 + P.n_terms) {
+        const int t = tid - 32;
+        double tc = P.coef[t];
+        for (int f = P.term_begin[t]; f < P.leaf_begin[t]; ++f) tc *= P.f[f].slot >= 0 ? theta[P.f[f].slot] : P.f[f].value;
+        S->tc[t] = tc;
+    }
 }
 
 // leaf value for one pair; `same_idx` = the two row indices are the same observation (Noise only)
@@ -80,6 +87,58 @@ __device__ __forceinline__ double leaf_deriv(int kind, double da, double k, doub
 //   SAME: Xa and Xb are the same observation set (K(X,X)): Noise = [gi == gj], diag_add goes on gi == gj,
 //         and indices >= na are the identity padding of the tiled factorisation (1 on the diagonal, 0 off it).
 //   !SAME: cross-covariance K(X, X*): Noise = 0, out-of-range entries = 0.
+// One leaf factor on an R x C block: k[r * C + c] = leaf(x_i[col], x_j[col]).
+template <int R, int C, bool SAME>
+__device__ __forceinline__ void leaf_block(const DevProgram &P, const ItemScalars &S, int f,
+                                           const double *__restrict__ Xa, int lda, const int (&ci)[R],
+                                           const double *__restrict__ Xb, int ldb, const int (&cj)[C],
+                                           const int (&gi)[R], const int (&gj)[C], double (&k)[R * C]) {
+    const int kind = P.f[f].kind;
+    if (kind == F_NOISE) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) k[r * C + c] = (SAME && gi[r] == gj[c]) ? 1.0 : 0.0;
+        return;
+    }
+    const double a = S.a[f];
+    const int col = P.f[f].col;
+    double xi[R], xj[C];
+#pragma unroll
+    for (int r = 0; r < R; ++r) xi[r] = Xa[(size_t)col * lda + ci[r]];
+#pragma unroll
+    for (int c = 0; c < C; ++c) xj[c] = Xb[(size_t)col * ldb + cj[c]];
+    if (kind == F_SQEXP) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double d = xi[r] - xj[c];
+                k[r * C + c] = a * (d * d);
+            }
+        fast_exp_vec<R * C>(k, S.etab);
+    } else if (kind == F_OU) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) k[r * C + c] = a * fabs(xi[r] - xj[c]);
+        fast_exp_vec<R * C>(k, S.etab);
+    } else if (kind == F_LINEAR) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) k[r * C + c] = fma(xi[r], xj[c], a);
+    } else {  // F_CAT
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) k[r * C + c] = (xi[r] == xj[c]) ? 1.0 : 0.0;
+    }
+}
+
+// out = sum_t tc_t prod_{leaves of t}.  The first leaf of a term is evaluated straight into the product and the
+// coefficient is applied by the closing FMA, so a single-leaf term (the common case) costs its leaf plus one FMA per
+// entry; keeping one accumulating array live across a factor loop instead cost 16-30 register moves per factor.
 template <int R, int C, bool SAME>
 __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
                                            int lda, int na, const int (&gi)[R], const double *__restrict__ Xb, int ldb,
@@ -96,92 +155,27 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
 
     for (int t = 0; t < P.n_terms; ++t) {
         if (!SAME && ((P.has_noise >> t) & 1)) continue;  // Noise terms vanish on cross-covariances
-        double prod[R][C];
-        const double coef = P.coef[t];
-        bool fresh = true;  // prod not materialised yet: the first factor writes coef * k instead of multiplying
-        for (int f = P.term_begin[t]; f < P.term_begin[t + 1]; ++f) {
-            const int kind = P.f[f].kind;
-            const double a = S.a[f];
-            if (kind == F_PARAM) {
-                if (fresh) {
-                    const double ca = coef * a;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] = ca;
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] *= a;
-                }
-            } else if (kind == F_NOISE) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        prod[r][c] = (SAME && gi[r] == gj[c]) ? (fresh ? coef : prod[r][c]) : 0.0;
-            } else {
-                const int col = P.f[f].col;
-                double xi[R], xj[C];
-#pragma unroll
-                for (int r = 0; r < R; ++r) xi[r] = Xa[(size_t)col * lda + ci[r]];
-#pragma unroll
-                for (int c = 0; c < C; ++c) xj[c] = Xb[(size_t)col * ldb + cj[c]];
-                if (kind == F_SQEXP || kind == F_OU) {
-                    double e[R * C];
-                    if (kind == F_SQEXP) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const double d = xi[r] - xj[c];
-                                e[r * C + c] = a * (d * d);
-                            }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) e[r * C + c] = a * fabs(xi[r] - xj[c]);
-                    }
-                    fast_exp_vec<R * C>(e, S.etab);
-                    if (fresh) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) prod[r][c] = coef * e[r * C + c];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) prod[r][c] *= e[r * C + c];
-                    }
-                } else if (kind == F_LINEAR) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            prod[r][c] = (fresh ? coef : prod[r][c]) * fma(xi[r], xj[c], a);
-                } else {  // F_CAT
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) prod[r][c] = (xi[r] == xj[c]) ? (fresh ? coef : prod[r][c]) : 0.0;
-                }
-            }
-            fresh = false;
-        }
-        if (fresh) {  // a term without factors: the bare coefficient
+        const double tc = S.tc[t];
+        const int f0 = P.leaf_begin[t], f1 = P.term_begin[t + 1];
+        if (f0 == f1) {  // a term without leaves: a per-item constant
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int c = 0; c < C; ++c) out[r][c] += coef;
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int c = 0; c < C; ++c) out[r][c] += prod[r][c];
+                for (int c = 0; c < C; ++c) out[r][c] += tc;
+            continue;
         }
+        double k[R * C];
+        leaf_block<R, C, SAME>(P, S, f0, Xa, lda, ci, Xb, ldb, cj, gi, gj, k);
+        for (int f = f0 + 1; f < f1; ++f) {
+            double e[R * C];
+            leaf_block<R, C, SAME>(P, S, f, Xa, lda, ci, Xb, ldb, cj, gi, gj, e);
+#pragma unroll
+            for (int q = 0; q < R * C; ++q) k[q] *= e[q];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[r][c] = fma(tc, k[r * C + c], out[r][c]);
     }
     if (SAME) {
 #pragma unroll

@@ -144,13 +144,18 @@ int compile_program(const gpl_op *ops, int n_ops, DevProgram *out, char *msg) {
     for (int t = 0; t < (int)p.size(); ++t) {
         out->term_begin[t] = nf;
         out->coef[t] = p[t].coef;
-        for (const DevFactor &f : p[t].fs) {
-            if (nf >= GPL_MAX_FACTORS) {
-                snprintf(msg, 160, "kernel-program: more than %d factors after expansion", GPL_MAX_FACTORS);
-                return GPL_ERR_LIMIT;
+        // per-item scalar factors first: the kernels fold them into one coefficient per term (kfun.cuh)
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) out->leaf_begin[t] = nf;
+            for (const DevFactor &f : p[t].fs) {
+                if ((f.kind == F_PARAM) != (pass == 0)) continue;
+                if (nf >= GPL_MAX_FACTORS) {
+                    snprintf(msg, 160, "kernel-program: more than %d factors after expansion", GPL_MAX_FACTORS);
+                    return GPL_ERR_LIMIT;
+                }
+                if (f.kind == F_NOISE) out->has_noise |= 1 << t;
+                out->f[nf++] = f;
             }
-            if (f.kind == F_NOISE) out->has_noise |= 1 << t;
-            out->f[nf++] = f;
         }
     }
     out->term_begin[p.size()] = nf;

@@ -29,6 +29,7 @@ struct DevProgram {
     int32_t n_theta;  // slots referenced
     int32_t n_cols;   // columns referenced
     int32_t term_begin[GPL_MAX_TERMS + 1];
+    int32_t leaf_begin[GPL_MAX_TERMS];  // factors [term_begin, leaf_begin) of a term are F_PARAM, the rest leaves
     int32_t has_noise;  // bit t set: term t contains an F_NOISE factor (zero off the diagonal and on cross-covariances)
     double coef[GPL_MAX_TERMS];
     DevFactor f[GPL_MAX_FACTORS];

@@ -1,7 +1,6 @@
-for v in "" _s4; do
-  if [ -n "$v" ]; then export GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so; fi
-  timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_v$v.json
-  python - <<PY
-import json; d=json.load(open('gpurun_out/bench_v$v.json')); print('$v', d['value'], d['ms_per_step'], d['roofline']['per_kernel_ms_per_step'])
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_pw.json
+python - <<'PY'
+import json; d=json.load(open('gpurun_out/bench_pw.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['per_kernel_ms_per_step'])
 PY
-done
