@@ -206,8 +206,10 @@ def kernel_flops(n: int, B: int):
     total = algorithmic_flops(n)
     tile3 = (n / nt) ** 3  # n need not be a multiple of 64: scale the tile cube so the parts sum to n^3/3
     scale = (n ** 3 / 3.0) / (tile3 * (nt / 3.0 + below_tiles + 2 * gemm + syrk))
-    f_below = scale * tile3 * (below_tiles + 2 * gemm) + 2.0 * n * n * below_tiles / ntri
-    f_diag = scale * tile3 * syrk + 2.0 * n * n * nt / ntri
+    # lk_below_kernel also forms the diagonal tiles of columns 1..nt-1 (syrk + their covariance entries);
+    # lk_diag_kernel is left with the covariance of tile (0, 0)
+    f_below = scale * tile3 * (below_tiles + 2 * gemm + syrk) + 2.0 * n * n * (below_tiles + nt - 1) / ntri
+    f_diag = 2.0 * n * n * 1 / ntri
     f_potrf = total - f_below - f_diag
     return {"below": B * f_below, "diag": B * f_diag, "potrf": B * f_potrf}
 

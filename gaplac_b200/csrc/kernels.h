@@ -28,9 +28,6 @@ __global__ void lml_batched_grad_kernel(const __grid_constant__ LmlParams prm); 
 size_t lml_smem_bytes(bool grad);
 
 // ---- batched lml, lockstep schedule (lml_lockstep.cu): three kernels per tile column over the whole batch ------------
-#ifndef GPL_LK_NSLOT
-#define GPL_LK_NSLOT 4  // shared-memory slots parking covariance quarters (kfun.cuh eval_block_acc_scr): 2 or 4
-#endif
 #ifndef GPL_LK_ZMAX
 #define GPL_LK_ZMAX 1024  // rows of z staged in shared memory by the diagonal-tile kernel
 #endif

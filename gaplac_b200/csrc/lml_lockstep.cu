@@ -27,9 +27,10 @@ namespace gpl {
 namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
-constexpr int LKC = 16;        // columns per pipeline stage
-constexpr int LCH = LKC * TS;  // doubles per operand stage; S = two stages of both operands = 32 KiB
-static_assert(4 * LCH == TILE_ELEMS, "two stages of both operands fill the staging buffer exactly");
+constexpr int LKC = 16;        // columns of one ring slot when it holds a single operand
+constexpr int LK_NS = 4;       // ring slots of the operand pipelines (cp.async groups, LK_NS - 1 stages in flight)
+constexpr int LCH = LKC * TS;  // doubles per ring slot (8 KiB); S = LK_NS slots = 32 KiB
+static_assert(LK_NS * LCH == TILE_ELEMS, "the ring fills the staging buffer exactly");
 
 struct __align__(16) StepSmem {
     double S[TILE_ELEMS];
@@ -84,73 +85,91 @@ __device__ __forceinline__ void diag_mma(double (&acc)[2][NCC], const double *__
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_constant__ LkParams prm) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StepSmem &sm = *reinterpret_cast<StepSmem *>(smem_raw);
+// Diagonal tile of column j of item b: covariance, update with the tiles (j, 0..j-1), right-hand side update.  Item
+// scalars must be ready in sm.sc (and a __syncthreads() must lie between that and this call).  Shared by lk_diag_kernel
+// (column 0) and lk_below_kernel, whose CTA for the tile (j, j-1) runs it as soon as that tile - the last input - is
+// stored: the fixed cost of this phase (covariance code, tile store: ~100 us per launch when it ran alone) then
+// overlaps the DMMA streams of the other CTAs instead of leaving the FP64 pipe idle.
+__device__ __forceinline__ void diag_tile_phase(const LkParams &prm, StepSmem &sm, int j, int b, int tid) {
     const DevProgram &P = prm.prog;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int warp = tid >> 5;
     const TMap tm = thread_map(tid);
-    const int n = prm.n, nt = prm.nt, j = prm.j, b = blockIdx.x;
+    const int n = prm.n, nt = prm.nt;
     const long long ntri = tri_index(nt, 0);
     double *wsL = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
     double *zb = prm.z + (size_t)b * nt * TS;
     const double *X = item_ptr(prm.X, prm.x_stride, b);
     const double *Y = item_ptr(prm.Y, prm.y_stride, b);
     const double diag_add = prm.sigma2[(size_t)b * prm.sigma2_stride] + prm.jitter;
-    prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
 
-    constexpr int DKC = 32, DCH = DKC * TS;  // only one operand is staged: two stages of 32 columns fill S
+    // only one operand is staged: a ring of LK_NS slots of 16 columns, LK_NS - 1 stages in flight (one barrier per stage)
+    constexpr int DKC = 16, DCH = DKC * TS;
+    static_assert(DCH == LCH, "one ring slot per stage");
     const int Q = (TS / DKC) * j;
     const double *srcA = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1) are contiguous
-    auto issue = [&](int s) {
-        block_load_async<DCH * 8>(sm.S + (s & 1) * DCH, srcA + (size_t)s * DCH, tid);
+    auto issue = [&](int s) {  // always commits, so that the group count tracks the stage number
+        if (s < Q) block_load_async<DCH * 8>(sm.S + (s % LK_NS) * DCH, srcA + (size_t)s * DCH, tid);
         cp_async_commit();
     };
     const bool z_in_smem = j * TS <= GPL_LK_ZMAX;
     if (z_in_smem)
         for (int t = tid; t < j * TS; t += NTHREADS) sm.zs[t] = zb[t];
     const double *zsrc = z_in_smem ? sm.zs : zb;
-    if (GPL_LK_NSLOT == 2 && Q > 0) issue(0);
-    __syncthreads();  // item scalars, z
-    const int rows[2] = {8 * warp + tm.g, 8 * (7 - warp) + tm.g};  // this kernel's row map
+    const int rows[2] = {8 * warp + tm.g, 8 * (7 - warp) + tm.g};  // this phase's row map
     double acc[2][NCC];
     {
         int gi[2] = {j * TS + rows[0], j * TS + rows[1]};
         // quarters of 16 columns: row block 7 - w needs columns up to 63 - 8w
-        // stage 0 of the update operands is in flight into the first half of S; the second half parks the quarters
-#if GPL_LK_NSLOT == 2
-        double *const slot[2] = {sm.S + 2 * LCH, sm.S + 3 * LCH};
-#else
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-#endif
-        eval_block_acc_scr<true, GPL_LK_NSLOT>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, slot, tid, acc,
-                                               (63 - 8 * warp) / 16 + 1);
-        if (GPL_LK_NSLOT == 4) {
-            __syncthreads();  // every thread has read its quarters back
-            if (Q > 0) issue(0);
-        }
+        eval_block_acc_scr<true, 4>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, slot, tid, acc,
+                                    (63 - 8 * warp) / 16 + 1);
+        __syncthreads();  // every thread has read its quarters back (and zs is complete)
+#pragma unroll
+        for (int s0 = 0; s0 < LK_NS - 1; ++s0) issue(s0);
     }
-    double ytmp = 0.0;
-    if (tid < TS) ytmp = (j * TS + tid < n) ? Y[j * TS + tid] : 0.0;
+    // right-hand side update y_j - sum_k L_jk z_k: every thread takes one row and half of a stage's columns, as two
+    // interleaved chains (a 32-long dependent DFMA chain in two warps only made the other two wait at the barrier:
+    // FP64 chains crawl while DMMA streams share the pipe, tools/pipe_mix.cu)
+    double yp0 = 0.0, yp1 = 0.0;
+    const int yrow = tid & (TS - 1), yhalf = (tid >> 6) * (DKC / 2);
     for (int q = 0; q < Q; ++q) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (q + 1 < Q) issue(q + 1);
-        const double *a = sm.S + (q & 1) * DCH;
+        cp_async_wait<LK_NS - 2>();  // stage q landed (for this thread's copies)
+        __syncthreads();             // ... for everyone's; and everyone is done with stage q - 1
+        issue(q + LK_NS - 1);        // into the slot of stage q - 1
+        const double *a = sm.S + (q % LK_NS) * DCH;
         switch (warp) {
         case 0: diag_mma<0, DKC>(acc, a, tm); break;
         case 1: diag_mma<1, DKC>(acc, a, tm); break;
         case 2: diag_mma<2, DKC>(acc, a, tm); break;
         default: diag_mma<3, DKC>(acc, a, tm); break;
         }
-        if (tid < TS) ytmp -= tile_row_dot(a, zsrc + q * DKC, tid, 0, DKC);
+        {
+            const double *zq = zsrc + q * DKC + yhalf;
+#pragma unroll
+            for (int k = 0; k < DKC / 2; k += 2) {
+                yp0 = fma(a[tidx(yrow, yhalf + k)], zq[k], yp0);
+                yp1 = fma(a[tidx(yrow, yhalf + k + 1)], zq[k + 1], yp1);
+            }
+        }
     }
     double *Tjj = wsL + tri_index(j, j) * TILE_ELEMS;
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) Tjj[tidx(rows[mb], col_of(tm, cc))] = acc[mb][cc];
-    if (tid < TS) zb[j * TS + tid] = ytmp;
+    __syncthreads();  // last stage consumed: S is free for the two partial sums per row
+    sm.S[tid] = yp0 + yp1;
+    __syncthreads();
+    if (tid < TS) zb[j * TS + tid] = ((j * TS + tid < n) ? Y[j * TS + tid] : 0.0) - (sm.S[tid] + sm.S[tid + TS]);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_constant__ LkParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem &sm = *reinterpret_cast<StepSmem *>(smem_raw);
+    const int tid = threadIdx.x, b = blockIdx.x;
+    prepare_item_scalars(prm.prog, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
+    __syncthreads();
+    diag_tile_phase(prm, sm, prm.j, b, tid);
 }
 
 // ---- Cholesky of the diagonal tiles of column j -----------------------------------------------------------------------
@@ -209,14 +228,18 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_potrf_kernel(const __grid_cons
 // is factored in registers (one row per lane, warp shuffles), inverted by forward substitution, the rows below are
 // solved against it in place, the right-hand side is advanced (z = L^-1 y), and the trailing lower blocks take their
 // rank-16 update through DMMA with accumulators loaded from / stored to the shared tile.
-constexpr int PW_WARPS = 6;
+constexpr int PW_WARPS = 7;
+// The warp's scratch lives in blocks of the tile that lie above the diagonal (rows 0..15 of columns >= 16 are never
+// part of L): the inverse of the current 16 x 16 block in columns 16..31 (row i of it in column 16 + i, rotated by 2i
+// so that "one row per lane" reads spread over the banks), the right-hand side in columns 32..35, the pivots in
+// 36..39, their reciprocal square roots in column 40.  That makes a GP cost exactly one 32 KiB tile: 7 per SM.
 struct __align__(16) PotrfWarpSmem {
     double T[TILE_ELEMS];
-    double W16[DBLK];
-    double y[TS];
-    double piv[TS];
-    double rs[16];
 };
+__device__ __forceinline__ int pw_w(int i, int k) { return (16 + i) * TS + ((k + 2 * i) & 15); }
+__device__ __forceinline__ int pw_y(int m) { return (32 + (m >> 4)) * TS + (m & 15); }
+__device__ __forceinline__ int pw_piv(int m) { return (36 + (m >> 4)) * TS + (m & 15); }
+__device__ __forceinline__ int pw_rs(int c) { return 40 * TS + c; }
 size_t lk_potrf_warp_smem_bytes() { return sizeof(PotrfWarpSmem) * PW_WARPS; }
 int lk_potrf_warp_items_per_cta() { return PW_WARPS; }
 
@@ -237,9 +260,11 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
         cp_async16(reinterpret_cast<char *>(sm.T) + idx * 16, reinterpret_cast<const char *>(Tjj) + idx * 16);
     }
     cp_async_commit();
-    sm.y[lane] = zb[j * TS + lane];
-    sm.y[lane + 32] = zb[j * TS + lane + 32];
+    const double y0 = zb[j * TS + lane], y1 = zb[j * TS + lane + 32];
     cp_async_wait<0>();
+    __syncwarp();
+    sm.T[pw_y(lane)] = y0;
+    sm.T[pw_y(lane + 32)] = y1;
     __syncwarp();
     int fail = -1;
     const int r_own = lane & 15;
@@ -258,8 +283,8 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
             }
             const double rs = rsqrt(piv);
             if (lane == 0) {
-                sm.piv[16 * p + c] = piv;
-                sm.rs[c] = rs;
+                sm.T[pw_piv(16 * p + c)] = piv;
+                sm.T[pw_rs(c)] = rs;
             }
             const double l = a[c] * rs;
             a[c] = (r_own >= c) ? l : 0.0;
@@ -282,17 +307,17 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
             for (int i = 0; i < 16; ++i) x[i] = (i == r_own) ? 1.0 : 0.0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                x[c] *= sm.rs[c];
+                x[c] *= sm.T[pw_rs(c)];
 #pragma unroll
                 for (int i = c + 1; i < 16; ++i) x[i] = fma(-sm.T[tidx(16 * p + i, 16 * p + c)], x[c], x[i]);
             }
             if (lane < 16) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) sm.W16[i * DLD + r_own] = x[i];
+                for (int i = 0; i < 16; ++i) sm.T[pw_w(i, r_own)] = x[i];
             }
         }
         __syncwarp();
-        for (int e = lane; e < DBLK; e += 32) Dg[p * DBLK + e] = sm.W16[e];
+        for (int e = lane; e < 256; e += 32) Dg[p * DBLK + (e >> 4) * DLD + (e & 15)] = sm.T[pw_w(e >> 4, e & 15)];
         // rows below the block: L[r, panel] = T[r, panel] * W16'   (in place, one row per lane, two passes)
         for (int r = 16 * (p + 1) + lane; r < TS; r += 32) {
             double pk[16], out[16];
@@ -303,7 +328,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int k2 = 0; k2 <= c / 2; ++k2) {  // W16 row c is zero beyond column c
-                    const double2 w = *reinterpret_cast<const double2 *>(&sm.W16[c * DLD + 2 * k2]);
+                    const double2 w = *reinterpret_cast<const double2 *>(&sm.T[pw_w(c, 2 * k2)]);
                     s0 = fma(pk[2 * k2], w.x, s0);
                     s1 = fma(pk[2 * k2 + 1], w.y, s1);
                 }
@@ -318,21 +343,21 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
             double z1 = 0.0;  // W16 row is zero beyond the diagonal: no triangular predicate needed
 #pragma unroll
             for (int k2 = 0; k2 < 8; ++k2) {
-                const double2 w = *reinterpret_cast<const double2 *>(&sm.W16[r_own * DLD + 2 * k2]);
-                const double2 yv = *reinterpret_cast<const double2 *>(&sm.y[16 * p + 2 * k2]);
+                const double2 w = *reinterpret_cast<const double2 *>(&sm.T[pw_w(r_own, 2 * k2)]);
+                const double2 yv = *reinterpret_cast<const double2 *>(&sm.T[pw_y(16 * p + 2 * k2)]);
                 zp = fma(w.x, yv.x, zp);
                 z1 = fma(w.y, yv.y, z1);
             }
             zp += z1;
         }
         __syncwarp();
-        if (lane < 16) sm.y[16 * p + lane] = zp;
+        if (lane < 16) sm.T[pw_y(16 * p + lane)] = zp;
         __syncwarp();
         for (int r = 16 * (p + 1) + lane; r < TS; r += 32) {
-            double s = sm.y[r];
+            double s = sm.T[pw_y(r)];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) s = fma(-sm.T[tidx(r, 16 * p + k)], sm.y[16 * p + k], s);
-            sm.y[r] = s;
+            for (int k = 0; k < 16; ++k) s = fma(-sm.T[tidx(r, 16 * p + k)], sm.T[pw_y(16 * p + k)], s);
+            sm.T[pw_y(r)] = s;
         }
         // trailing lower blocks (8 x 8): T[rb, cb] -= L[rb, panel] L[cb, panel]'
         for (int rb = 2 * (p + 1); rb < 8; ++rb) {
@@ -372,10 +397,10 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
         const int idx = it * 32 + lane;
         reinterpret_cast<double2 *>(Tjj)[idx] = reinterpret_cast<const double2 *>(sm.T)[idx];
     }
-    const double z0 = sm.y[lane], z1 = sm.y[lane + 32];
+    const double z0 = sm.T[pw_y(lane)], z1 = sm.T[pw_y(lane + 32)];
     zb[j * TS + lane] = z0;
     zb[j * TS + lane + 32] = z1;
-    double zq = fma(z0, z0, z1 * z1), lg = log(sm.piv[lane]) + log(sm.piv[lane + 32]);
+    double zq = fma(z0, z0, z1 * z1), lg = log(sm.T[pw_piv(lane)]) + log(sm.T[pw_piv(lane + 32)]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         zq += __shfl_xor_sync(0xffffffffu, zq, o);
@@ -415,22 +440,23 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     }
     prepare_item_scalars(P, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
 
-    const int Q = (TS / LKC) * j;  // update steps (even)
+    // Operand ring: LK_NS slots of 8 KiB.  Update stage s < Q holds 8 columns of both operands (A = tiles (i, 0..j-1),
+    // B = tiles (j, 0..j-1)); the three stages after the last update hold columns 0..47 of L_jj as 16-column chunks for
+    // the triangular solve.  LK_NS - 1 stages are in flight; one barrier per stage.
+    constexpr int RKC = 8, RCH = RKC * TS;
+    static_assert(2 * RCH == LCH && LK_NS * LCH == TILE_ELEMS, "ring slots fill S");
+    const int Q = (TS / RKC) * j;
     const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1)
-    const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1), then L_jj itself
+    const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1)
     const double *srcL = wsL + tri_index(j, j) * TILE_ELEMS;
-    // The four 8 KiB slots of S: A0 = S, A1 = S + LCH, B0 = S + 2 LCH, B1 = S + 3 LCH.  Update step s uses (A, B)[s & 1].
-    // The triangular solve needs columns 0..47 of L_jj as three chunks: chunk 0 -> B0, chunk 1 -> A0 (both free while the
-    // last update step runs out of A1 / B1), chunk 2 -> B1 once that step is done.
-    auto issue = [&](int s) {  // update step s < Q
-        const int st = (s & 1) * LCH;
-        block_load_async<LCH * 8>(sm.S + st, srcA + (size_t)s * LCH, tid);
-        block_load_async<LCH * 8>(sm.S + 2 * LCH + st, srcB + (size_t)s * LCH, tid);
-        cp_async_commit();
-    };
-    auto issue_l01 = [&]() {
-        block_load_async<LCH * 8>(sm.S + 2 * LCH, srcL, tid);
-        block_load_async<LCH * 8>(sm.S, srcL + LCH, tid);
+    auto issue = [&](int s) {  // always commits, so that the group count tracks the stage number
+        double *dst = sm.S + (s % LK_NS) * LCH;
+        if (s < Q) {
+            block_load_async<RCH * 8>(dst, srcA + (size_t)s * RCH, tid);
+            block_load_async<RCH * 8>(dst + RCH, srcB + (size_t)s * RCH, tid);
+        } else if (s < Q + 3) {
+            block_load_async<LCH * 8>(dst, srcL + (size_t)(s - Q) * LCH, tid);
+        }
         cp_async_commit();
     };
     // block inverses of L_jj ride in the first commit group
@@ -438,12 +464,6 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         const double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
         static_assert(DSIZE * 8 % (16 * NTHREADS) == 0, "D in whole 16-byte chunks per thread");
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
-    }
-    if (GPL_LK_NSLOT == 2) {
-        if (Q > 0) issue(0);
-        else issue_l01();
-    } else {
-        cp_async_commit();
     }
     __syncthreads();  // item scalars
     double acc[2][NCC];
@@ -453,41 +473,43 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
-#if GPL_LK_NSLOT == 2
-        double *const slot[2] = {sm.S + LCH, sm.S + 3 * LCH};  // A1 / B1: not written before update step 1 is issued
-#else
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-#endif
-        eval_block_acc_scr<false, GPL_LK_NSLOT>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
-        if (GPL_LK_NSLOT == 4) {
-            __syncthreads();
-            if (Q > 0) issue(0);
-            else issue_l01();
+        eval_block_acc_scr<false, 4>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
+        __syncthreads();  // quarters read back: S is free for the ring
+    }
+#pragma unroll
+    for (int s0 = 0; s0 < LK_NS - 1; ++s0) issue(s0);  // D rides in the first group
+    for (int q = 0; q < Q; ++q) {
+        cp_async_wait<LK_NS - 2>();
+        __syncthreads();
+        issue(q + LK_NS - 1);
+        const double *a = sm.S + (q % LK_NS) * LCH;
+        tile_mma<true>(acc, a, a + RCH, tm, 0, RKC);
+    }
+    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels; chunk c of L_jj is ring stage Q + c
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        cp_async_wait<LK_NS - 2>();
+        __syncthreads();
+        issue(Q + c + LK_NS - 1);  // nothing left to load: an empty group keeps the count in step
+        const double *l = sm.S + ((Q + c) % LK_NS) * LCH;
+        if (c == 0) {
+            trsm_rl_solve<0>(acc, sm.D, tm);
+            trsm_rl_update<0>(acc, l, tm);
+        } else if (c == 1) {
+            trsm_rl_solve<1>(acc, sm.D, tm);
+            trsm_rl_update<1>(acc, l, tm);
+        } else {
+            trsm_rl_solve<2>(acc, sm.D, tm);
+            trsm_rl_update<2>(acc, l, tm);
         }
     }
-    for (int q = 0; q < Q; ++q) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (q + 1 < Q) issue(q + 1);
-        else issue_l01();  // q = Q - 1 is odd: slots A0 / B0 are free
-        const double *a = sm.S + (q & 1) * LCH;
-        tile_mma<true>(acc, a, a + 2 * LCH, tm, 0, LKC);
-    }
-    // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels
-    cp_async_wait<0>();
-    __syncthreads();  // chunks 0, 1 (and D) landed; slots A1 / B1 free
-    block_load_async<LCH * 8>(sm.S + 3 * LCH, srcL + 2 * LCH, tid);
-    cp_async_commit();
-    trsm_rl_solve<0>(acc, sm.D, tm);
-    trsm_rl_update<0>(acc, sm.S + 2 * LCH, tm);
-    trsm_rl_solve<1>(acc, sm.D, tm);
-    trsm_rl_update<1>(acc, sm.S, tm);
-    trsm_rl_solve<2>(acc, sm.D, tm);
-    cp_async_wait<0>();
-    __syncthreads();
-    trsm_rl_update<2>(acc, sm.S + 3 * LCH, tm);
     trsm_rl_solve<3>(acc, sm.D, tm);
     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
+    if (i == j + 1) {      // the tile just stored completes row j + 1: its diagonal tile can be formed now
+        __syncthreads();   // the stores above are visible to the whole CTA; S is free
+        diag_tile_phase(prm, sm, j + 1, b, tid);
+    }
 }
 
 }  // namespace gpl
