@@ -254,17 +254,24 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
     double *Tjj = prm.tiles + ((size_t)b * ntri + tri_index(j, j)) * TILE_ELEMS;
     double *zb = prm.z + (size_t)b * nt * TS;
     double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
-#pragma unroll 8
-    for (int it = 0; it < TILE_BYTES / 16 / 32; ++it) {
-        const int idx = it * 32 + lane;
-        cp_async16(reinterpret_cast<char *>(sm.T) + idx * 16, reinterpret_cast<const char *>(Tjj) + idx * 16);
+    // Only the lower part of the tile moves: rows 16p..63 of the 16 columns of panel p (62.5 % of the tile; the rows
+    // above stay scratch).  One cp.async group per panel: the first 16 x 16 block is factored while panels 1..3 land.
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cpc = 32 - 8 * pp;  // 16-byte chunks per column
+#pragma unroll
+        for (int it = 0; it < (16 * (32 - 8 * pp)) / 32; ++it) {
+            const int q = it * 32 + lane, col = q / cpc, off = q - col * cpc;
+            const int e = (16 * pp + col) * TS + 16 * pp + 2 * off;
+            cp_async16(sm.T + e, Tjj + e);
+        }
+        cp_async_commit();
     }
-    cp_async_commit();
-    const double y0 = zb[j * TS + lane], y1 = zb[j * TS + lane + 32];
-    cp_async_wait<0>();
-    __syncwarp();
-    sm.T[pw_y(lane)] = y0;
-    sm.T[pw_y(lane + 32)] = y1;
+    sm.T[pw_y(lane)] = zb[j * TS + lane];
+    sm.T[pw_y(lane + 32)] = zb[j * TS + lane + 32];
+    cp_async_wait<3>();
     __syncwarp();
     int fail = -1;
     const int r_own = lane & 15;
@@ -337,6 +344,16 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
 #pragma unroll
             for (int c = 0; c < 16; ++c) sm.T[tidx(r, 16 * p + c)] = out[c];
         }
+        if (p == 0) cp_async_wait<0>();  // panels 1..3 are needed from here on
+        __syncwarp();
+        {  // panel p is final (L): rows 16p..63 of its columns go home now, spreading the stores over the kernel
+            const int cpc = 32 - 8 * p;
+            for (int q = lane; q < 16 * cpc; q += 32) {
+                const int col = q / cpc, off = q - col * cpc;
+                const int e = (16 * p + col) * TS + 16 * p + 2 * off;
+                *reinterpret_cast<double2 *>(Tjj + e) = *reinterpret_cast<const double2 *>(sm.T + e);
+            }
+        }
         // right-hand side: z_p = W16 y_p, then y_below -= L[below, panel] z_p
         double zp = 0.0;
         {
@@ -391,12 +408,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
         }
         __syncwarp();
     }
-    // results: L_jj in place, z_j, running z'z and logdet, failure report, lml after the last column
-#pragma unroll 8
-    for (int it = 0; it < TILE_BYTES / 16 / 32; ++it) {
-        const int idx = it * 32 + lane;
-        reinterpret_cast<double2 *>(Tjj)[idx] = reinterpret_cast<const double2 *>(sm.T)[idx];
-    }
+    // results: z_j, running z'z and logdet, failure report, lml after the last column (L_jj went home panel by panel)
     const double z0 = sm.T[pw_y(lane)], z1 = sm.T[pw_y(lane + 32)];
     zb[j * TS + lane] = z0;
     zb[j * TS + lane + 32] = z1;

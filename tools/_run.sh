@@ -1,6 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_pw.json
-python - <<'PY'
-import json; d=json.load(open('gpurun_out/bench_pw.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['per_kernel_ms_per_step'], d['roofline']['frac'], d['roofline']['whole_step']['frac'], d['gpu_launches'])
-PY
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_potrf_warp -s 10 -c 1 -o gpurun_out/pw2 -f python bench.py --steps 2 --warmup 1 > gpurun_out/ncu.log 2>&1
+ls -la gpurun_out/pw2.ncu-rep
