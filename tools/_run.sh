@@ -1,3 +1,5 @@
 set -x
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lk_potrf_warp -s 10 -c 1 -o gpurun_out/pw2 -f python bench.py --steps 2 --warmup 1 > gpurun_out/ncu.log 2>&1
-ls -la gpurun_out/pw2.ncu-rep
+timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r01.err | tail -1 > gpurun_out/bench_r01.json || exit 1
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_r01_ref.json
+timeout 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:lk_ -s 16 -c 16 --csv --log-file gpurun_out/launches_r01_lockstep.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
+timeout 600 python tools/bench_configs.py > gpurun_out/configs_r01.json 2>gpurun_out/configs_r01.err

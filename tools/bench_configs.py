@@ -57,8 +57,8 @@ def fit():
     post[0] = ctx.posterior_fit(prog, d["X"], d["y"], d["theta"], 0.0)
 
 
-tf = best(fit, 2)
-tp = best(lambda: post[0].mean_and_var(d["Xs"]), 2)
+tf = best(fit, 6)
+tp = best(lambda: post[0].mean_and_var(d["Xs"]), 4)
 n, m = 2048, 20000
 out["C4 posterior fit n=2048"] = {"ms": tf * 1e3, "tflops": n ** 3 / 3 / tf * 1e-12}
 out["C4 predict 20000 points"] = {"ms": tp * 1e3, "points_per_s": m / tp, "tflops": (n * n * m + 2 * n * m) / tp * 1e-12}
