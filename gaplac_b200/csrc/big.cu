@@ -188,29 +188,51 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         long long tb = clock64();
         t_wait_panel += tb - ta;
 #endif
-        if (j > 0) wait_flag_ge(rowdone + j, j, tid);
-#ifdef GPL_BIG_PROFILE
-        t_wait_row += clock64() - tb;
-#endif
+        // In-panel left-looking update of the diagonal tile.  Everything but the last term is applied BEFORE waiting
+        // for tile (j, j-1) - the only input that is still being produced (by the column kernel of column j-1, which
+        // started when L_{j-1,j-1} was published) - so that only one 64-column update and the factorisation itself sit
+        // on the serial path.
         double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
+        double acc[2][NCC];
+        if (j - k0 >= 2) wait_flag_ge(rowdone + j, j - 1, tid);  // tiles (j, k0..j-2) are final (normally long since)
         __syncthreads();
         tile_load_async(sm.A, Tjj, tid);
-        if (j > k0) tile_load_async(sm.Bt, prm.tiles + tri_index(j, k0) * TILE_ELEMS, tid);
         cp_async_commit();
-        cp_async_wait<0>();
+        if (j - k0 >= 2) {
+            tile_load_async(sm.Bt, prm.tiles + tri_index(j, k0) * TILE_ELEMS, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        double acc[2][NCC];
         acc_from_tile(acc, sm.A, tm);
-        for (int k = k0; k < j; ++k) {  // in-panel left-looking update; tile k sits in Bt / A alternately
+        for (int k = k0; k < j - 1; ++k) {  // tile k sits in Bt / A alternately
             double *cur = ((k - k0) & 1) ? sm.A : sm.Bt;
             double *nxt = ((k - k0) & 1) ? sm.Bt : sm.A;
-            __syncthreads();  // everyone done reading `nxt` (previous step / accumulator load)
-            if (k + 1 < j) {
+            cp_async_wait<0>();
+            __syncthreads();  // tile k landed; everyone done reading `nxt` (previous step / accumulator load)
+            if (k + 1 < j - 1) {
                 tile_load_async(nxt, prm.tiles + tri_index(j, k + 1) * TILE_ELEMS, tid);
                 cp_async_commit();
             }
             tile_mma<true>(acc, cur, cur, tm, 0, TS);
+        }
+#ifdef GPL_BIG_PROFILE
+        long long tc = clock64();
+#endif
+        if (j > 0) wait_flag_ge(rowdone + j, j, tid);
+#ifdef GPL_BIG_PROFILE
+        t_wait_row += clock64() - tc;
+#endif
+        if (j > k0) {  // the last term: tile (j, j-1)
+            double *cur = ((j - 1 - k0) & 1) ? sm.A : sm.Bt;
+            __syncthreads();
+            tile_load_async(cur, prm.tiles + tri_index(j, j - 1) * TILE_ELEMS, tid);
+            cp_async_commit();
             cp_async_wait<0>();
+            __syncthreads();
+            tile_mma<true>(acc, cur, cur, tm, 0, TS);
         }
         __syncthreads();
         const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
@@ -254,9 +276,8 @@ __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
     __syncthreads();
     double acc[2][NCC];
     acc_from_tile(acc, sm.A, tm);
-    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, W_jj, z_j stored; tiles (j, k0..j-1) were final before that
-    tile_load_async(sm.W, prm.winv + (size_t)j * TILE_ELEMS, tid);
-    cp_async_commit();
+    // in-panel update first: its inputs - tiles (i, k) and (j, k), k0 <= k < j - were final before this kernel was
+    // launched (stream order behind the previous column's kernel), so it overlaps the worker's factorisation of L_jj
     for (int k = prm.k0; k < j; ++k) {
         __syncthreads();
         tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
@@ -266,6 +287,9 @@ __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
         __syncthreads();
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
+    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, W_jj, z_j stored
+    tile_load_async(sm.W, prm.winv + (size_t)j * TILE_ELEMS, tid);
+    cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
     tile_trsm_w(acc, sm.W, tm);
