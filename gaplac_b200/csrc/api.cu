@@ -376,11 +376,11 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     const size_t diag_smem = 200 * 1024;
     std::vector<cudaEvent_t> eF(NP), eB(NP);
     for (int P = 0; P < NP; ++P) {
-        CU(ctx, cudaEventCreateWithFlags(&eF[P], cudaEventDisableTiming));
-        CU(ctx, cudaEventCreateWithFlags(&eB[P], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&eF[P], ctx->profile_events == 2 ? cudaEventDefault : cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&eB[P], ctx->profile_events == 2 ? cudaEventDefault : cudaEventDisableTiming));
     }
     cudaEvent_t e0, eW;
-    CU(ctx, cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&e0, ctx->profile_events == 2 ? cudaEventDefault : cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&eW, cudaEventDisableTiming));
     CU(ctx, cudaEventRecord(e0, st));
     CU(ctx, cudaStreamWaitEvent(ctx->s_panel, e0, 0));
@@ -425,6 +425,15 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     CU(ctx, cudaStreamWaitEvent(st, eB[NP - 2], 0));
     if (use_worker) CU(ctx, cudaStreamWaitEvent(st, eW, 0));
     CU(ctx, cudaGetLastError());
+    if (ctx->profile_events == 2) {  // debug: when each panel was factored / its trailing update finished (ms from start)
+        CU(ctx, cudaStreamSynchronize(st));
+        for (int P = 0; P < NP; ++P) {
+            float tf = 0.f, tb = 0.f;
+            cudaEventElapsedTime(&tf, e0, eF[P]);
+            if (P + 1 < NP) cudaEventElapsedTime(&tb, e0, eB[P]);
+            fprintf(stderr, "panel %2d factored %.3f  trail done %.3f\n", P, tf, tb);
+        }
+    }
     for (int P = 0; P < NP; ++P) {
         cudaEventDestroy(eF[P]);
         cudaEventDestroy(eB[P]);

@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 120 python tools/run_c5.py 2048 2 2>&1 | tail -1
 timeout 120 python tools/run_c5.py 8192 3 2>&1 | tail -2
 timeout 120 python tools/run_c5.py 4096 3 2>&1 | tail -1
-timeout 120 python tools/run_c5.py 2048 3 2>&1 | tail -1
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

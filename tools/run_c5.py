@@ -4,7 +4,7 @@ import numpy as np
 from gaplac_b200 import _lib, workloads as W
 import ctypes as C
 ctx = _lib.Context(0)
-ctx.set_option('profile_events', 1)
+ctx.set_option('profile_events', int(os.environ.get('PROF', '1')))
 if os.environ.get('CHOLV'): ctx.set_option('chol_variant', int(os.environ['CHOLV']))
 lib = _lib.load(); lib.gpl_debug_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
