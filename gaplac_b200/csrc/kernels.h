@@ -28,6 +28,9 @@ __global__ void lml_batched_grad_kernel(const __grid_constant__ LmlParams prm); 
 size_t lml_smem_bytes(bool grad);
 
 // ---- batched lml, lockstep schedule (lml_lockstep.cu): three kernels per tile column over the whole batch ------------
+#ifndef GPL_LK_CW
+#define GPL_LK_CW 4  // covariance entries per row and interpretation step in the lockstep kernels (4 or 8)
+#endif
 #ifndef GPL_LK_ZMAX
 #define GPL_LK_ZMAX 1024  // rows of z staged in shared memory by the diagonal-tile kernel
 #endif

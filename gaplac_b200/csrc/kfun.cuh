@@ -258,37 +258,48 @@ __device__ __forceinline__ void eval_block_acc(const DevProgram &P, const ItemSc
 // 20 % of the j = 0 launch stalled on instruction fetch), and each quarter parks its 8 values in a thread-private
 // column of a shared-memory slot (NTHREADS x 8 doubles = 8 KiB, conflict-free, no barrier needed) from where they are
 // read back into statically indexed accumulator registers.  NSLOT slots -> 4 / NSLOT passes.
-template <bool SAME, int NSLOT>
+template <bool SAME, int NSLOT, int CW = 4>
 __device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const ItemScalars &S,
                                                    const double *__restrict__ Xa, int lda, int na, const int (&gi)[2],
                                                    const double *__restrict__ Xb, int ldb, int nb, int cbase, int t,
                                                    double diag_add, double *const (&slot)[NSLOT], int tid,
                                                    double (&out)[2][16], int hmax = 4) {
+    // CW = 4: the code runs per quarter (2 x 4 entries, 16 columns of the tile); CW = 8: per half (2 x 8 entries), which
+    // halves the per-step interpretation / load / bookkeeping instructions and doubles the independent exp chains.
     static_assert(NSLOT == 1 || NSLOT == 2 || NSLOT == 4, "slots");
+    static_assert(CW == 4 || CW == 8, "entries per row and step");
+    constexpr int STEPS = 16 / CW;          // steps per tile
+    constexpr int SPS = CW / 4;             // slots per step (a slot parks 8 values per thread)
+    constexpr int STEPS_PER_PASS = NSLOT / SPS;
+    static_assert(STEPS_PER_PASS >= 1, "a step must fit the slots");
+    const int smax = (hmax + SPS - 1) / SPS;
 #pragma unroll
-    for (int pass = 0; pass < 4 / NSLOT; ++pass) {
+    for (int pass = 0; pass < STEPS / STEPS_PER_PASS; ++pass) {
 #pragma unroll 1
-        for (int hh = 0; hh < NSLOT; ++hh) {
-            const int h = pass * NSLOT + hh;
-            int gjh[4];
-            double o[2][4];
+        for (int ss = 0; ss < STEPS_PER_PASS; ++ss) {
+            const int st = pass * STEPS_PER_PASS + ss;
+            int gjh[CW];
+            double o[2][CW];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
-            if (h < hmax) {
-                eval_block<2, 4, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+            for (int c = 0; c < CW; ++c) gjh[c] = cbase + 4 * CW * st + 8 * (c >> 1) + 2 * t + (c & 1);
+            if (st < smax) {
+                eval_block<2, CW, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
             } else {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
+                    for (int c = 0; c < CW; ++c) o[r][c] = 0.0;
             }
-            double *dst = slot[0];
 #pragma unroll
-            for (int q = 1; q < NSLOT; ++q) dst = (hh == q) ? slot[q] : dst;
+            for (int u = 0; u < SPS; ++u) {  // slot ss * SPS + u takes columns 4u..4u+3 of the step
+                double *dst = slot[u];
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+                for (int q = 1; q < STEPS_PER_PASS; ++q) dst = (ss == q) ? slot[q * SPS + u] : dst;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) dst[(r * 4 + c) * 128 + tid] = o[r][c];
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[(r * 4 + c) * 128 + tid] = o[r][4 * u + c];
+            }
         }
 #pragma unroll
         for (int hh = 0; hh < NSLOT; ++hh)

@@ -121,7 +121,7 @@ __device__ __forceinline__ void diag_tile_phase(const LkParams &prm, StepSmem &s
         int gi[2] = {j * TS + rows[0], j * TS + rows[1]};
         // quarters of 16 columns: row block 7 - w needs columns up to 63 - 8w
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-        eval_block_acc_scr<true, 4>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, slot, tid, acc,
+        eval_block_acc_scr<true, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, diag_add, slot, tid, acc,
                                     (63 - 8 * warp) / 16 + 1);
         __syncthreads();  // every thread has read its quarters back (and zs is complete)
 #pragma unroll
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-        eval_block_acc_scr<false, 4>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
+        eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
         __syncthreads();  // quarters read back: S is free for the ring
     }
 #pragma unroll
