@@ -1,7 +1,4 @@
-for v in "" _cw8; do
-  if [ -n "$v" ]; then export GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so; fi
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_v$v.json
-  python - <<PY
-import json; d=json.load(open('gpurun_out/bench_v$v.json')); print('$v', d['value'], d['ms_per_step'], d['roofline']['per_kernel_ms_per_step'], d['arms_max_rel_diff'])
-PY
-done
+set -x
+timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/b.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lk_below|lk_potrf_warp" -s 22 -c 2 -o gpurun_out/r01_final -f python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
+ls -la gpurun_out/r01_final.ncu-rep
