@@ -25,15 +25,16 @@ for ln in open(dis, errors="replace"):
         addr2line[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(src_csv)))
 # split into launches at header rows
-launches, curl, hdr = [], None, None
+launches, hdrs, curl = [], [], None
 for r in rows:
     if r and r[0] == "Address":
-        hdr = r
+        hdrs.append(r)
         curl = []
         launches.append(curl)
     elif curl is not None and r and re.match(r"^[0-9a-fx]+$", r[0]):
         curl.append(r)
 L = launches[which]
+hdr = hdrs[which]
 isrc, iex, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 base = int(L[0][0], 16)
 ops = defaultdict(int)
