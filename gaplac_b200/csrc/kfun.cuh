@@ -13,7 +13,8 @@ namespace gpl {
 // per-item scalars derived from theta once per CTA (shared memory)
 struct ItemScalars {
     double a[GPL_MAX_FACTORS];   // SQEXP: -1/(2 l^2); OU: -1/l; LINEAR: c; PARAM: theta
-    double da[GPL_MAX_FACTORS];  // derivative scale: SQEXP 1/l^3 (dk = k d^2 / l^3); OU 1/l^2 (dk = k |d| / l^2)
+    double da[GPL_MAX_FACTORS];  // derivative scale: SQEXP 1/l^3 (dk = k d^2 / l^3); OU 1/l^2 (dk = k |d| / l^2);
+                                 // PARAM: the term's coefficient without this factor
     double tc[GPL_MAX_TERMS];    // per term: coef * prod of its F_PARAM factors
     double etab[64];             // 2^(j/64) for fast_exp (fastexp.h), copied from constant memory once per CTA
 };
@@ -33,6 +34,13 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
             a = -1.0 / h;
             da = 1.0 / (h * h);
         }
+        if (f.kind == F_PARAM) {  // d term / d theta_f = (coef * the term's other per-item scalars) * product of its leaves
+            int t = 0;
+            while (tid >= P.term_begin[t + 1]) ++t;
+            da = P.coef[t];
+            for (int g = P.term_begin[t]; g < P.leaf_begin[t]; ++g)
+                if (g != tid) da *= P.f[g].slot >= 0 ? theta[P.f[g].slot] : P.f[g].value;
+        }
         S->a[tid] = a;
         S->da[tid] = da;
     }
@@ -42,43 +50,6 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
         double tc = P.coef[t];
         for (int f = P.term_begin[t]; f < P.leaf_begin[t]; ++f) tc *= P.f[f].slot >= 0 ? theta[P.f[f].slot] : P.f[f].value;
         S->tc[t] = tc;
-    }
-}
-
-// leaf value for one pair; `same_idx` = the two row indices are the same observation (Noise only)
-__device__ __forceinline__ double leaf_value(int kind, double a, double xi, double xj, bool same_idx) {
-    switch (kind) {
-    case F_SQEXP: {
-        double d = xi - xj;
-        return exp(a * (d * d));
-    }
-    case F_OU:
-        return exp(a * fabs(xi - xj));
-    case F_LINEAR:
-        return fma(xi, xj, a);
-    case F_CAT:
-        return xi == xj ? 1.0 : 0.0;
-    case F_NOISE:
-        return same_idx ? 1.0 : 0.0;
-    default:  // F_PARAM
-        return a;
-    }
-}
-
-// d leaf / d (its own hyperparameter), given the leaf value k
-__device__ __forceinline__ double leaf_deriv(int kind, double da, double k, double xi, double xj) {
-    switch (kind) {
-    case F_SQEXP: {
-        double d = xi - xj;
-        return k * (d * d) * da;
-    }
-    case F_OU:
-        return k * fabs(xi - xj) * da;
-    case F_LINEAR:
-    case F_PARAM:
-        return 1.0;
-    default:
-        return 0.0;
     }
 }
 
@@ -310,46 +281,111 @@ __device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const It
     }
 }
 
-// Contract a weight block w[r][c] with dK/dtheta_s for every slot s:  g[s] += sum_rc w[r][c] dK[r][c]/dtheta_s.
-// gsum: shared-memory accumulators (GPL_MAX_THETA doubles); one atomicAdd per (term, factor-with-slot, warp).
-template <int R, int C>
-__device__ __forceinline__ void contract_grad_block(const DevProgram &P, const ItemScalars &S,
-                                                    const double *__restrict__ X, int ldx, int n, const int (&gi)[R],
-                                                    const int (&gj)[C], const double (&w)[R][C], double *gsum) {
-    int ci[R], cj[C];
+// Contract a weight block with dK/dtheta_s for every slot s:  g[s] += sum_rc w[r][c] dK[r][c]/dtheta_s, for the 2 x 4
+// entries rows gi x columns gj of K(X, X).  Every leaf of a term is evaluated once (fast_exp, 8 wide); a term
+// T = tc * prod_leaves k contributes
+//   per-item scalar factor f (variance, Constant):  da_f * sum w prod_leaves k
+//   SqExp / OU length scale:                         tc * da_f * sum w (prod_leaves k) d^2   (resp. |d|)
+//   Linear offset c:                                 tc * sum w prod_{leaves != f} k
+// gsum: shared-memory accumulators (GPL_MAX_THETA doubles); one atomicAdd per (term, factor with a slot, warp).
+__device__ __forceinline__ void grad_reduce_add(double part, double *dst) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) ci[r] = gi[r] < n ? gi[r] : n - 1;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dst, part);
+}
+__device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const ItemScalars &S,
+                                                      const double *__restrict__ X, int ldx, int n, const int (&gi)[2],
+                                                      const int (&gj)[4], const double (&w)[8], double *gsum) {
+    int ci[2], cj[4];
 #pragma unroll
-    for (int c = 0; c < C; ++c) cj[c] = gj[c] < n ? gj[c] : n - 1;
+    for (int r = 0; r < 2; ++r) ci[r] = gi[r] < n ? gi[r] : n - 1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cj[c] = gj[c] < n ? gj[c] : n - 1;
+    double wm[8];  // weights, zero outside the matrix
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wm[r * 4 + c] = (gi[r] < n && gj[c] < n) ? w[r * 4 + c] : 0.0;
     for (int t = 0; t < P.n_terms; ++t) {
-        for (int f = P.term_begin[t]; f < P.term_begin[t + 1]; ++f) {
-            const int slot = P.f[f].slot;
-            if (slot < 0) continue;
-            double part = 0.0;
+        const int p0 = P.term_begin[t], f0 = P.leaf_begin[t], f1 = P.term_begin[t + 1];
+        bool any = false;
+        for (int f = p0; f < f1; ++f) any = any || P.f[f].slot >= 0;
+        if (!any) continue;
+        double wl[8];  // w * product of the term's leaves
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+        for (int e = 0; e < 8; ++e) wl[e] = wm[e];
+        for (int f = f0; f < f1; ++f) {
+            double k[8];
+            leaf_block<2, 4, true>(P, S, f, X, ldx, ci, X, ldx, cj, gi, gj, k);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (gi[r] >= n || gj[c] >= n) continue;
-                    double v = P.coef[t];
-                    const bool same = gi[r] == gj[c];
-                    for (int g = P.term_begin[t]; g < P.term_begin[t + 1]; ++g) {
-                        const DevFactor fg = P.f[g];
-                        double xi = 0.0, xj = 0.0;
-                        if (fg.kind <= F_CAT) {
-                            xi = X[(size_t)fg.col * ldx + ci[r]];
-                            xj = X[(size_t)fg.col * ldx + cj[c]];
-                        }
-                        double k = leaf_value(fg.kind, S.a[g], xi, xj, same);
-                        v *= (g == f) ? leaf_deriv(fg.kind, S.da[g], k, xi, xj) : k;
-                    }
-                    part = fma(w[r][c], v, part);
-                }
-            // warp reduction, then one shared-memory atomic per warp
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&gsum[slot], part);
+            for (int e = 0; e < 8; ++e) wl[e] *= k[e];
         }
+        double sl = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sl += wl[e];
+        for (int f = p0; f < f0; ++f)  // per-item scalar factors
+            if (P.f[f].slot >= 0) grad_reduce_add(S.da[f] * sl, &gsum[P.f[f].slot]);
+        const double tc = S.tc[t];
+        for (int f = f0; f < f1; ++f) {
+            const int slot = P.f[f].slot, kind = P.f[f].kind;
+            if (slot < 0) continue;
+            const int col = P.f[f].col;
+            double part = 0.0;
+            if (kind == F_SQEXP || kind == F_OU) {
+                double xi[2], xj[4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) xi[r] = X[(size_t)col * ldx + ci[r]];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) xj[c] = X[(size_t)col * ldx + cj[c]];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double d = xi[r] - xj[c];
+                        part = fma(wl[r * 4 + c], kind == F_SQEXP ? d * d : fabs(d), part);
+                    }
+                part *= tc * S.da[f];
+            } else if (kind == F_LINEAR) {  // dk/dc = 1: the product of the other leaves
+                double wo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) wo[e] = wm[e];
+                for (int g = f0; g < f1; ++g) {
+                    if (g == f) continue;
+                    double k[8];
+                    leaf_block<2, 4, true>(P, S, g, X, ldx, ci, X, ldx, cj, gi, gj, k);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) wo[e] *= k[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) part += wo[e];
+                part *= tc;
+            }
+            grad_reduce_add(part, &gsum[slot]);
+        }
+    }
+}
+
+// The 2 x 16 block of one thread (rows gi, columns cbase + col_of): the weights are parked in thread-private columns of
+// a 32 KiB shared-memory scratch so that one rolled copy of the quarter code serves all four quarters.
+__device__ __forceinline__ void contract_grad_block(const DevProgram &P, const ItemScalars &S,
+                                                    const double *__restrict__ X, int ldx, int n, const int (&gi)[2],
+                                                    int cbase, int t, const double (&w)[2][16], double *scratch, int tid,
+                                                    double *gsum) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) scratch[(r * 16 + cc) * 128 + tid] = w[r][cc];
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+        int gjh[4];
+        double wq[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gjh[c] = cbase + 16 * h + 8 * (c >> 1) + 2 * t + (c & 1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wq[r * 4 + c] = scratch[(r * 16 + 4 * h + c) * 128 + tid];
+        contract_grad_quarter(P, S, X, ldx, n, gi, gjh, wq, gsum);
     }
 }
 

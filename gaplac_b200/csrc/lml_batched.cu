@@ -349,7 +349,8 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                 for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
                     for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = sym * (acc[mb][cc] - wsAl[gi[mb]] * wsAl[gj[cc]]);
-                contract_grad_block<2, NCC>(P, sm.sc, X, n, n, gi, gj, acc, sm.gsum);
+                __syncthreads();  // the tiles in S / Bt are consumed: S parks the weights
+                contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum);
             }
         }
         __syncthreads();

@@ -1,4 +1,4 @@
-set -x
-timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/b.log 2>&1 || exit 1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lk_below|lk_potrf_warp" -s 22 -c 2 -o gpurun_out/r01_final -f python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
-ls -la gpurun_out/r01_final.ncu-rep
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/bench_configs.py 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin)
+for k,v in d.items(): print(k, {a: round(b,3) for a,b in v.items()})"
