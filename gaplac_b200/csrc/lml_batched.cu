@@ -64,9 +64,11 @@ constexpr double LOG2PI = 1.8378770664093454835606594728112;
 template <bool GRAD>
 struct __align__(16) LmlSmem {
     double S[TILE_ELEMS];
+    // Gradient kernel: a second whole-tile buffer for the K^-1 phases.  Until those start it hosts D and zs (below), which
+    // keeps the kernel at three CTAs per SM (it ran at two: 12 % of the warp slots, DMMA pipe 41 % busy).
     double Bt[GRAD ? TILE_ELEMS : 2];
-    double D[DSIZE];  // inverses of the four 16 x 16 diagonal blocks of the current diagonal tile
-    double zs[GPL_LML_ZMAX];  // z = L^-1 y of the current item (global workspace instead when n is larger)
+    double Dbuf[GRAD ? 2 : DSIZE];         // inverses of the four 16 x 16 diagonal blocks of the current diagonal tile
+    double zbuf[GRAD ? 2 : GPL_LML_ZMAX];  // z = L^-1 y of the current item (global workspace instead when n is larger)
     ItemScalars sc;
     double rsbuf[16];
     double pivbuf[TS];
@@ -87,6 +89,36 @@ __device__ __forceinline__ void block_indices(const TMap &tm, int i, int j, int 
     for (int cc = 0; cc < NCC; ++cc) gj[cc] = j * TS + col_of(tm, cc);
 }
 
+// acc (+/-)= sum_{k0 <= k < k1} A_k B_k' over whole tiles, both operands streamed in 16-column chunks through a 4-stage
+// cp.async ring (ring = 64 KiB: stage = 8 KiB of A + 8 KiB of B; three stages in flight, one barrier per stage).
+// srcA(k) / srcB(k) give the tiles; `same`: B_k is A_k (one copy is loaded).
+template <bool SUB, class FA, class FB>
+__device__ __forceinline__ void ring_tile_mma(double (&acc)[2][NCC], double *ring, FA srcA, FB srcB, int k0, int k1,
+                                              bool same, const TMap &tm, int tid) {
+    constexpr int RCH = 16 * TS, NS = 4;  // doubles per operand chunk, stages
+    const int Q = 4 * (k1 - k0);
+    auto issue = [&](int s) {
+        if (s < Q) {
+            const int k = k0 + (s >> 2), c = s & 3;
+            double *dst = ring + (s % NS) * 2 * RCH;
+            block_load_async<RCH * 8>(dst, srcA(k) + c * RCH, tid);
+            if (!same) block_load_async<RCH * 8>(dst + RCH, srcB(k) + c * RCH, tid);
+        }
+        cp_async_commit();
+    };
+    __syncthreads();  // the ring is free
+#pragma unroll
+    for (int s = 0; s < NS - 1; ++s) issue(s);
+    for (int s = 0; s < Q; ++s) {
+        cp_async_wait<NS - 2>();
+        __syncthreads();
+        issue(s + NS - 1);
+        const double *a = ring + (s % NS) * 2 * RCH;
+        tile_mma<SUB>(acc, a, same ? a : a + RCH, tm, 0, 16);
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace
 
 template <bool GRAD>
@@ -103,7 +135,10 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
     double *wsW = wsL + ntri * TILE_ELEMS;                      // inverses of the diagonal tiles
     double *wsM = wsW + (size_t)nt * TILE_ELEMS;                // (L^-1)' tiles (gradient only)
     double *wsZg = prm.vec + (size_t)blockIdx.x * 2 * nt * TS;  // z = L^-1 y (global copy: alpha phase, large n)
-    double *wsZ = (nt * TS <= GPL_LML_ZMAX) ? sm.zs : wsZg;
+    double *const smD = GRAD ? sm.Bt : sm.Dbuf;
+    double *const smZ = GRAD ? sm.Bt + DSIZE : sm.zbuf;
+    static_assert(DSIZE + GPL_LML_ZMAX <= TILE_ELEMS, "D and zs fit the second tile buffer");
+    double *wsZ = (nt * TS <= GPL_LML_ZMAX) ? smZ : wsZg;
     double *wsAl = wsZg + (size_t)nt * TS;                      // alpha = K^-1 y
 
     PH_DECL;
@@ -176,14 +211,14 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                 PH_MARK(2);
                 if (diag) {
                     __syncthreads();  // S becomes the factorisation scratch
-                    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+                    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, smD, sm.rsbuf, sm.pivbuf, tid);
                     PH_MARK(3);
                     if (tid == 0 && fail >= 0 && sm.info == 0) sm.info = j * TS + fail + 1;
                     acc_to_tile(wsL + tri_index(j, j) * TILE_ELEMS, acc, tm);
                     __syncthreads();  // scratch no longer read
                     acc_to_tile(sm.S, acc, tm);  // L_jj in shared memory for the forward solve (and the inverse)
                     if (tid < TS) sm.ybuf[tid] = ytmp;
-                    tile_forward_solve(sm.S, sm.D, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
+                    tile_forward_solve(sm.S, smD, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
                     if (tid < TS) {
                         wsZ[j * TS + tid] = sm.ybuf[tid];
                         if (wsZ != wsZg && (prm.want_grad || prm.keep)) wsZg[j * TS + tid] = sm.ybuf[tid];
@@ -201,7 +236,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
                             for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
-                        tile_trsm_ld(e, sm.S, sm.D, tm);
+                        tile_trsm_ld(e, sm.S, smD, tm);
                         acc_to_tile_t(wsW + (size_t)j * TILE_ELEMS, e, tm);
                     }
                     PH_MARK(4);
@@ -215,23 +250,23 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    tile_trsm_ld(acc, sm.S, sm.D, tm);
+                    tile_trsm_ld(acc, sm.S, smD, tm);
 #else
-                    trsm_rl_solve<0>(acc, sm.D, tm);
+                    trsm_rl_solve<0>(acc, smD, tm);
                     cp_async_wait<0>();
                     __syncthreads();
                     issue(Q + 1);
                     trsm_rl_update<0>(acc, sm.S + 2 * LCH, tm);
-                    trsm_rl_solve<1>(acc, sm.D, tm);
+                    trsm_rl_solve<1>(acc, smD, tm);
                     cp_async_wait<0>();
                     __syncthreads();
                     issue(Q + 2);
                     trsm_rl_update<1>(acc, sm.S + 3 * LCH, tm);
-                    trsm_rl_solve<2>(acc, sm.D, tm);
+                    trsm_rl_solve<2>(acc, smD, tm);
                     cp_async_wait<0>();
                     __syncthreads();
                     trsm_rl_update<2>(acc, sm.S + 2 * LCH, tm);
-                    trsm_rl_solve<3>(acc, sm.D, tm);
+                    trsm_rl_solve<3>(acc, smD, tm);
 #endif
                     PH_MARK(5);
                     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
@@ -303,15 +338,9 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
                     continue;
                 }
                 acc_zero(acc);
-                for (int k = j; k < i; ++k) {
-                    __syncthreads();
-                    tile_load_async(sm.S, wsL + tri_index(i, k) * TILE_ELEMS, tid);
-                    tile_load_async(sm.Bt, wsM + tri_index(k, j) * TILE_ELEMS, tid);
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    __syncthreads();
-                    tile_mma<false>(acc, sm.S, sm.Bt, tm, 0, TS);  // S += L_ik M_kj
-                }
+                ring_tile_mma<false>(  // S += L_ik M_kj
+                    acc, sm.S, [&](int k) { return wsL + tri_index(i, k) * TILE_ELEMS; },
+                    [&](int k) { return wsM + tri_index(k, j) * TILE_ELEMS; }, j, i, false, tm, tid);
                 // M_ij = -W_ii S : row operand W_ii, column operand S' (transposed store of the accumulator)
                 __syncthreads();
                 tile_load_async(sm.S, wsW + (size_t)i * TILE_ELEMS, tid);
@@ -333,15 +362,9 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
             for (int i = j; i < nt; ++i) {
                 double acc[2][NCC];
                 acc_zero(acc);
-                for (int k = i; k < nt; ++k) {
-                    __syncthreads();
-                    tile_load_async(sm.S, wsM + tri_index(k, i) * TILE_ELEMS, tid);
-                    if (i != j) tile_load_async(sm.Bt, wsM + tri_index(k, j) * TILE_ELEMS, tid);
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    __syncthreads();
-                    tile_mma<false>(acc, sm.S, (i == j) ? sm.S : sm.Bt, tm, 0, TS);
-                }
+                ring_tile_mma<false>(
+                    acc, sm.S, [&](int k) { return wsM + tri_index(k, i) * TILE_ELEMS; },
+                    [&](int k) { return wsM + tri_index(k, j) * TILE_ELEMS; }, i, nt, i == j, tm, tid);
                 int gi[2], gj[NCC];
                 block_indices(tm, i, j, gi, gj);
                 const double sym = (i == j) ? 1.0 : 2.0;
