@@ -39,7 +39,7 @@ struct gpl_ctx {
     char name[128] = {0};
     cudaStream_t stream = nullptr;
     cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
-    DevBuf bigFlags;
+    DevBuf bigFlags, bigD;
     uint64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -312,6 +312,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     BigParams prm;
     prm.tiles = tiles;
     prm.winv = winv;
+    prm.dblk = nullptr;
     prm.pivlog = pivlog;
     prm.info = dinfo;
     prm.y = y;
@@ -367,11 +368,14 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, lo));
         CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
     int rc = ensure(ctx, ctx->bigFlags, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int));
     if (rc) return rc;
     prm.flags = ptr<int>(ctx->bigFlags);
+    if ((rc = ensure(ctx, ctx->bigD, (size_t)nt * DSIZE * sizeof(double)))) return rc;
+    prm.dblk = ptr<double>(ctx->bigD);
     CU(ctx, cudaMemsetAsync(prm.flags, 0, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int), st));
     const size_t diag_smem = 200 * 1024;
     std::vector<cudaEvent_t> eF(NP), eB(NP);
@@ -423,7 +427,11 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     }
     CU(ctx, cudaStreamWaitEvent(st, eF[NP - 1], 0));
     CU(ctx, cudaStreamWaitEvent(st, eB[NP - 2], 0));
-    if (use_worker) CU(ctx, cudaStreamWaitEvent(st, eW, 0));
+    if (use_worker) {
+        CU(ctx, cudaStreamWaitEvent(st, eW, 0));
+        big_winv_kernel<<<nt, NTHREADS, smem, st>>>(prm);
+        ctx->launches++;
+    }
     CU(ctx, cudaGetLastError());
     if (ctx->profile_events == 2) {  // debug: when each panel was factored / its trailing update finished (ms from start)
         CU(ctx, cudaStreamSynchronize(st));
@@ -511,7 +519,7 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)

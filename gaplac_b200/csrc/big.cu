@@ -237,22 +237,19 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         __syncthreads();
         const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
         if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
+        // Publish L_jj and the inverses of its 16 x 16 diagonal blocks; that is all the column kernel needs for its solve.
+        // The full inverse W_jj (backward substitution, posterior) is formed after the factorisation by big_winv_kernel,
+        // off this serial path.
         acc_to_tile(Tjj, acc, tm);
-        __syncthreads();
-        acc_to_tile(sm.A, acc, tm);
-        if (prm.y && tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
-        __syncthreads();
-        double e[2][NCC];
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-            for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
-        tile_trsm_ld(e, sm.A, sm.D, tm);
-        acc_to_tile_t(sm.W, e, tm);
-        __syncthreads();
-        tile_store(prm.winv + (size_t)j * TILE_ELEMS, sm.W, tid);
+        for (int t = tid; t < DSIZE; t += NTHREADS) prm.dblk[(size_t)j * DSIZE + t] = sm.D[t];
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
-        if (prm.y && tid < TS) prm.y[j * TS + tid] = tile_row_dot(sm.W, sm.ybuf, tid, 0, tid + 1);
+        if (prm.y) {
+            __syncthreads();
+            acc_to_tile(sm.A, acc, tm);
+            if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+            tile_forward_solve(sm.A, sm.D, sm.ybuf, sm.rsbuf, tid);  // z_j = L_jj^-1 y_j
+            if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+        }
         __threadfence();
         __syncthreads();
         if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;
@@ -287,12 +284,13 @@ __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
         __syncthreads();
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
-    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, W_jj, z_j stored
-    tile_load_async(sm.W, prm.winv + (size_t)j * TILE_ELEMS, tid);
+    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, its block inverses and z_j are stored
+    tile_load_async(sm.W, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
+    block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    tile_trsm_w(acc, sm.W, tm);
+    tile_trsm_ld(acc, sm.W, sm.D, tm);
     acc_to_tile(Tij, acc, tm);
     if (prm.y) {
         __syncthreads();
@@ -304,6 +302,26 @@ __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
     __threadfence();
     __syncthreads();
     if (tid == 0) *reinterpret_cast<volatile int *>(rowdone + i) = j + 1;
+}
+
+// W_jj = L_jj^-1 for every diagonal tile at once (worker protocol: the serial path only produced the block inverses)
+__global__ void __launch_bounds__(NTHREADS) big_winv_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, j = blockIdx.x;
+    const TMap tm = thread_map(tid);
+    tile_load_async(sm.A, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
+    block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double e[2][NCC];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+    tile_trsm_ld(e, sm.A, sm.D, tm);
+    acc_to_tile_t(prm.winv + (size_t)j * TILE_ELEMS, e, tm);
 }
 
 // trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'

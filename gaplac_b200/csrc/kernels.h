@@ -92,6 +92,7 @@ __global__ void tiles_to_upper_kernel(const double *__restrict__ tiles, int n, i
 struct BigParams {
     double *tiles;  // lower tiles, in place: A on entry, L on exit
     double *winv;   // nt tiles: inverses of the diagonal tiles
+    double *dblk;   // nt x DSIZE: inverses of the 16 x 16 diagonal blocks (worker protocol; NULL otherwise)
     double *pivlog; // nt * 64 doubles: log of the pivots
     int *info;      // single int, first failing pivot (1-based) or 0
     double *y;      // optional padded right-hand side (nt*64): y on entry, z = L^-1 y on exit; NULL to skip
@@ -112,7 +113,8 @@ __global__ void big_col_kernel(BigParams prm);    // nt - j - 1 CTAs
 __global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (i >= l, l0 <= l < l1)
 // look-ahead protocol: one persistent CTA factors every diagonal tile in turn; the column kernel waits for it per column
 __global__ void big_worker_kernel(BigParams prm);    // 1 CTA for the whole factorisation (owns an SM)
-__global__ void big_col_flag_kernel(BigParams prm);  // nt - j - 1 CTAs; spins on diagdone[j], publishes rowdone[i]
+__global__ void big_col_flag_kernel(BigParams prm);
+__global__ void big_winv_kernel(BigParams prm);  // grid nt: W_jj = L_jj^-1 from L_jj and its block inverses  // nt - j - 1 CTAs; spins on diagdone[j], publishes rowdone[i]
 size_t big_smem_bytes();
 size_t big_trail_smem_bytes();
 
