@@ -15,22 +15,22 @@ namespace gpl {
 
 namespace {
 struct __align__(16) PredSmem {
-    double A[TILE_ELEMS];
+    double A[TILE_ELEMS];  // at the end of a slab its first 16 KiB take the 32 partial column sums per column
     double Bt[TILE_ELEMS];
-    double part[32 * TS];  // per (row band, lane group) partial column sums
     ItemScalars sc;
 };
 }  // namespace
 
 size_t predict_smem_bytes() { return sizeof(PredSmem); }
 
-__global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_constant__ PredictParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_constant__ PredictParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PredSmem &sm = *reinterpret_cast<PredSmem *>(smem_raw);
     const DevProgram &P = prm.prog;
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
     const int n = prm.n, nt = prm.nt, m = prm.m;
+    double *const part = sm.A;  // 32 * TS doubles, used between the tile loops only
     double *wsV = prm.wsV + (size_t)blockIdx.x * nt * TILE_ELEMS;
     prepare_item_scalars(P, prm.theta, &sm.sc, tid);
     __syncthreads();
@@ -85,23 +85,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) predict_kernel(const __grid_const
         const int slot = (tid >> 5) * 8 + tm.g;
         __syncthreads();
 #pragma unroll
-        for (int cc = 0; cc < NCC; ++cc) sm.part[slot * TS + col_of(tm, cc)] = cmean[cc];
+        for (int cc = 0; cc < NCC; ++cc) part[slot * TS + col_of(tm, cc)] = cmean[cc];
         __syncthreads();
         if (tid < TS && s * TS + tid < m) {
             double sum = 0.0;
 #pragma unroll 8
-            for (int gq = 0; gq < 32; ++gq) sum += sm.part[gq * TS + tid];
+            for (int gq = 0; gq < 32; ++gq) sum += part[gq * TS + tid];
             prm.mean[s * TS + tid] = sum;
         }
         if (prm.want_var) {
             __syncthreads();
 #pragma unroll
-            for (int cc = 0; cc < NCC; ++cc) sm.part[slot * TS + col_of(tm, cc)] = csq[cc];
+            for (int cc = 0; cc < NCC; ++cc) part[slot * TS + col_of(tm, cc)] = csq[cc];
             __syncthreads();
             if (tid < TS && s * TS + tid < m) {
                 double sum = 0.0;
 #pragma unroll 8
-                for (int gq = 0; gq < 32; ++gq) sum += sm.part[gq * TS + tid];
+                for (int gq = 0; gq < 32; ++gq) sum += part[gq * TS + tid];
                 // prior variance of the latent function at x*: Noise contributes 0 (SAME = false)
                 int one_i[1] = {s * TS + tid}, one_j[1] = {s * TS + tid};
                 double kss[1][1];
