@@ -440,7 +440,19 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     const TMap tm = thread_map(tid);
     const int n = prm.n, nt = prm.nt, j = prm.j;
     const int nbelow = nt - 1 - j;
-    const int b = blockIdx.x / nbelow, i = j + 1 + blockIdx.x % nbelow;  // the tiles of one GP are neighbours (L2 reuse)
+    // Block order: first the B CTAs of row j + 1 (they also form the next diagonal tile and run about twice as long:
+    // started first, they are not what the last wave waits for), then the other rows, the tiles of one GP next to each
+    // other (L2 reuse of its row-j operand).
+    const int Bn = gridDim.x / nbelow;
+    int b, i;
+    if ((int)blockIdx.x < Bn) {
+        b = blockIdx.x;
+        i = j + 1;
+    } else {
+        const int r = blockIdx.x - Bn;
+        b = r / (nbelow - 1);
+        i = j + 2 + r % (nbelow - 1);
+    }
     const long long ntri = tri_index(nt, 0);
     double *wsL = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
     const double *X = item_ptr(prm.X, prm.x_stride, b);
