@@ -14,6 +14,12 @@
 #include "kernels.h"
 #include "tile.cuh"
 
+#ifndef GPL_TRAIL_KC
+#define GPL_TRAIL_KC 16  // columns per stage of the trailing-update ring
+#define GPL_TRAIL_NS 3   // ring slots (48 KiB: still four CTAs per SM; measured n = 8192: 16 x 3 -> 7.90 ms, 16 x 2 -> 8.05,
+                         // 8 x 4 -> 8.25, 16 x 4 (three CTAs per SM) -> 8.27; the LDGSTS ring it replaced: 8.07)
+#endif
+
 namespace gpl {
 
 namespace {
@@ -325,10 +331,14 @@ __global__ void __launch_bounds__(NTHREADS) big_winv_kernel(BigParams prm) {
 }
 
 // trailing tiles (i, l), i >= l >= j1: T_il -= sum_{k0 <= k < j1} L_ik L_lk'
+// Operands move with bulk asynchronous copies (cp.async.bulk, one instruction per 4 KiB chunk, issued by thread 0) through
+// a ring of slots; "full" mbarriers (transaction bytes) hand a slot to the consumers, "empty" mbarriers (one arrival per
+// warp) hand it back, so the warps run decoupled: there is no block barrier in the loop.
 __global__ void __launch_bounds__(NTHREADS, 4) big_trail_kernel(BigParams prm) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *S = reinterpret_cast<double *>(smem_raw);  // two stages of 16 columns of both operands (32 KiB)
-    constexpr int KC = 16, CH = KC * TS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *S = reinterpret_cast<double *>(smem_raw);  // NS slots of KC columns of both operands
+    constexpr int KC = GPL_TRAIL_KC, CH = KC * TS, NS = GPL_TRAIL_NS;
+    __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
     const int tid = threadIdx.x;
     const TMap tm = thread_map(tid);
     // linear block index -> tile (i, l), l0 <= l < l1, l <= i < nt (column by column)
@@ -343,27 +353,44 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_trail_kernel(BigParams prm) {
     const int Q = (TS / KC) * (prm.j1 - prm.k0);  // the panel's tiles of a tile row are contiguous
     const double *srcA = prm.tiles + tri_index(i, prm.k0) * TILE_ELEMS;
     const double *srcB = prm.tiles + tri_index(l, prm.k0) * TILE_ELEMS;
-    block_load_async<CH * 8>(S, srcA, tid);
-    if (!diag) block_load_async<CH * 8>(S + 2 * CH, srcB, tid);
-    cp_async_commit();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int s) {  // thread 0 only
+        const int slot = s % NS;
+        double *dst = S + slot * 2 * CH;
+        mbar_arrive_expect_tx(&full_bar[slot], (diag ? 1u : 2u) * CH * 8u);
+        bulk_load(dst, srcA + (size_t)s * CH, CH * 8, &full_bar[slot]);
+        if (!diag) bulk_load(dst + CH, srcB + (size_t)s * CH, CH * 8, &full_bar[slot]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < NS - 1 && s < Q; ++s) issue(s);
     double acc[2][NCC];
     acc_from_tile(acc, Til, tm);  // straight from global / L2 into the accumulator registers
     for (int q = 0; q < Q; ++q) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (q + 1 < Q) {
-            const int nb = ((q + 1) & 1) * CH;
-            block_load_async<CH * 8>(S + nb, srcA + (size_t)(q + 1) * CH, tid);
-            if (!diag) block_load_async<CH * 8>(S + 2 * CH + nb, srcB + (size_t)(q + 1) * CH, tid);
-            cp_async_commit();
+        if (tid == 0 && q + NS - 1 < Q) {
+            // slot of stage q - 1: every warp has finished reading it (its use number (q - 1) / NS)
+            if (q >= 1) mbar_wait(&empty_bar[(q - 1) % NS], ((q - 1) / NS) & 1);
+            issue(q + NS - 1);
         }
-        const double *a = S + (q & 1) * CH;
-        const double *bt = diag ? a : a + 2 * CH;
-        tile_mma<true>(acc, a, bt, tm, 0, KC);
+        mbar_wait(&full_bar[q % NS], (q / NS) & 1);
+        const double *a = S + (q % NS) * 2 * CH;
+        tile_mma<true>(acc, a, diag ? a : a + CH, tm, 0, KC);
+        // generic-proxy reads of the slot must be ordered before the async-proxy refill: without this fence the bulk copy
+        // overwrote chunks that a warp was still reading (wrong factors at n = 8192, run-to-run different)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[q % NS]);
     }
     acc_to_tile(Til, acc, tm);
 }
-size_t big_trail_smem_bytes() { return TILE_BYTES; }
+size_t big_trail_smem_bytes() { return (size_t)GPL_TRAIL_NS * 2 * GPL_TRAIL_KC * TS * 8; }
 
 // backward substitution, one launch per tile row i (descending), grid = i + 1: every CTA recomputes
 // alpha_i = W_ii' r_i (r_i is final and read-only in this launch), CTA j < i applies r_j -= L_ij' alpha_i,

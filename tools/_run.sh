@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python tools/bench_configs.py 2>/dev/null | python -c "
-import json,sys; d=json.load(sys.stdin)
-for k,v in d.items(): print(k, {a: round(b,3) for a,b in v.items()})"
+timeout 60 python tools/run_c5.py 8192 3 2>&1 | tail -1
+timeout 60 python tools/run_c5.py 2048 2 2>&1 | tail -1
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for i in 1 2 3; do timeout 60 python tools/run_c5.py 8192 2 2>&1 | tail -1 | cut -c1-60; done
