@@ -1,4 +1,7 @@
-timeout 60 python tools/run_c5.py 8192 3 2>&1 | tail -1
-timeout 60 python tools/run_c5.py 2048 2 2>&1 | tail -1
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for i in 1 2 3; do timeout 60 python tools/run_c5.py 8192 2 2>&1 | tail -1 | cut -c1-60; done
+for v in "" _nosync; do
+  if [ -n "$v" ]; then export GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so; fi
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_v$v.json
+  python - <<PY
+import json; d=json.load(open('gpurun_out/bench_v$v.json')); print('$v', d['value'], d['ms_per_step'], d['roofline']['per_kernel_ms_per_step'], d['not_pd_items'])
+PY
+done
