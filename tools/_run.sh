@@ -1,7 +1,6 @@
-for v in "" _nosync; do
-  if [ -n "$v" ]; then export GAPLAC_B200_LIB=$PWD/gaplac_b200/libgaplac_b200$v.so; fi
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_v$v.json
-  python - <<PY
-import json; d=json.load(open('gpurun_out/bench_v$v.json')); print('$v', d['value'], d['ms_per_step'], d['roofline']['per_kernel_ms_per_step'], d['not_pd_items'])
-PY
-done
+set -x
+timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r01.err | tail -1 > gpurun_out/bench_r01.json || exit 1
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_r01_ref.json
+timeout 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:lk_ -s 16 -c 16 --csv --log-file gpurun_out/launches_r01_lockstep.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
+timeout 600 python tools/bench_configs.py > gpurun_out/configs_r01.json 2>gpurun_out/configs_r01.err
+CHOLV=3 timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:big_ -c 400 --csv --log-file gpurun_out/launches_r01_c5.csv python tools/run_c5.py 8192 1 > gpurun_out/ncu_c5.log 2>&1
