@@ -40,6 +40,8 @@ struct gpl_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
     DevBuf bigFlags, bigD;
+    std::vector<std::pair<void *, size_t>> postFree;  // device blocks of freed posteriors (cudaMalloc / cudaFree cost
+                                                      // milliseconds next to multi-GB workspaces: a refit reuses them)
     uint64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -65,6 +67,8 @@ struct gpl_post {
     int n = 0, d = 0, nt = 0, p = 0;
     double *dX = nullptr, *dtheta = nullptr;
     double *tiles = nullptr, *winv = nullptr, *alpha = nullptr;
+    void *block = nullptr;  // one device allocation behind dX | dtheta | tiles | alpha (recycled through the context)
+    size_t block_bytes = 0;
     double lml = 0.0;
 };
 
@@ -524,6 +528,7 @@ int gpl_destroy(gpl_ctx *ctx) {
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (auto &blk : ctx->postFree) cudaFree(blk.first);
     if (ctx->s_worker) cudaStreamDestroy(ctx->s_worker);
     if (ctx->s_panel) cudaStreamDestroy(ctx->s_panel);
     if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
@@ -708,15 +713,27 @@ int gpl_debug_phase_profile(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, co
 }
 
 // ---- posterior ---------------------------------------------------------------------------------------------------
+static void posterior_release(gpl_post *post) {  // caller holds the context lock (or there is no context)
+    gpl_ctx *ctx = post->ctx;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (post->block) {
+        if (ctx && ctx->postFree.size() < 8) {
+            cudaStreamSynchronize(ctx->stream);  // nothing in flight reads it any more
+            ctx->postFree.emplace_back(post->block, post->block_bytes);
+        } else {
+            cudaFree(post->block);
+        }
+    }
+    delete post;
+}
 int gpl_posterior_free(gpl_post *post) {
     if (!post) return GPL_OK;
-    if (post->ctx) cudaSetDevice(post->ctx->device);
-    cudaFree(post->dX);
-    cudaFree(post->dtheta);
-    cudaFree(post->tiles);
-    cudaFree(post->winv);
-    cudaFree(post->alpha);
-    delete post;
+    if (post->ctx) {
+        std::lock_guard<std::mutex> lk(post->ctx->mu);
+        posterior_release(post);
+    } else {
+        posterior_release(post);
+    }
     return GPL_OK;
 }
 
@@ -732,13 +749,32 @@ static int posterior_fit_impl(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, 
     post->nt = nt;
     post->p = p;
     int rc;
-    CU(ctx, cudaMalloc(&post->dX, (size_t)n * d * 8));
-    CU(ctx, cudaMalloc(&post->dtheta, (size_t)(p + 1) * 8));
-    // tiles and the diagonal inverses are one allocation-compatible layout with the fused kernel's workspace:
-    // [ntri L tiles][nt W tiles]
-    CU(ctx, cudaMalloc(&post->tiles, (size_t)(ntri + nt) * TILE_BYTES));
-    post->winv = nullptr;
-    CU(ctx, cudaMalloc(&post->alpha, (size_t)2 * nt * TS * 8));  // [z | alpha]
+    {
+        // one block: [tiles: ntri L tiles + nt W tiles (the fused kernel's workspace layout)] [z | alpha] [X] [theta]
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t b_tiles = up((size_t)(ntri + nt) * TILE_BYTES), b_alpha = up((size_t)2 * nt * TS * 8),
+                     b_x = up((size_t)n * d * 8), b_th = up((size_t)(p + 1) * 8);
+        const size_t need = b_tiles + b_alpha + b_x + b_th;
+        int best = -1;
+        for (int k = 0; k < (int)ctx->postFree.size(); ++k)
+            if (ctx->postFree[k].second >= need && ctx->postFree[k].second <= 2 * need &&
+                (best < 0 || ctx->postFree[k].second < ctx->postFree[best].second))
+                best = k;
+        if (best >= 0) {
+            post->block = ctx->postFree[best].first;
+            post->block_bytes = ctx->postFree[best].second;
+            ctx->postFree.erase(ctx->postFree.begin() + best);
+        } else {
+            CU(ctx, cudaMalloc(&post->block, need));
+            post->block_bytes = need;
+        }
+        char *base = static_cast<char *>(post->block);
+        post->tiles = reinterpret_cast<double *>(base);
+        post->alpha = reinterpret_cast<double *>(base + b_tiles);
+        post->dX = reinterpret_cast<double *>(base + b_tiles + b_alpha);
+        post->dtheta = reinterpret_cast<double *>(base + b_tiles + b_alpha + b_x);
+        post->winv = nullptr;
+    }
     CU(ctx, cudaMemcpyAsync(post->dX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
     if (p > 0) CU(ctx, cudaMemcpyAsync(post->dtheta, theta, (size_t)p * 8, cudaMemcpyHostToDevice, st));
     double *winv = post->tiles + ntri * TILE_ELEMS;
@@ -811,7 +847,7 @@ int gpl_posterior_fit(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const do
     rc = posterior_fit_impl(ctx, prog, n, d, X, y, theta, p, sigma2, jitter, post);
     if (rc) {
         cudaStreamSynchronize(ctx->stream);
-        gpl_posterior_free(post);
+        posterior_release(post);
         return rc;
     }
     *out = post;
@@ -930,7 +966,7 @@ int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X
         }
     }
     cudaStreamSynchronize(ctx->stream);
-    gpl_posterior_free(post);
+    posterior_release(post);
     return rc;
 }
 

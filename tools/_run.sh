@@ -1,6 +1,4 @@
-set -x
-timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r01.err | tail -1 > gpurun_out/bench_r01.json || exit 1
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_r01_ref.json
-timeout 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:lk_ -s 16 -c 16 --csv --log-file gpurun_out/launches_r01_lockstep.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
-timeout 600 python tools/bench_configs.py > gpurun_out/configs_r01.json 2>gpurun_out/configs_r01.err
-CHOLV=3 timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:big_ -c 400 --csv --log-file gpurun_out/launches_r01_c5.csv python tools/run_c5.py 8192 1 > gpurun_out/ncu_c5.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/bench_configs.py 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin)
+for k,v in d.items(): print(k, {a: round(b,3) for a,b in v.items()})"
