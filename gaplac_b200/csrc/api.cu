@@ -271,8 +271,11 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
             if (ctx->lml_variant == 2) {
                 lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);  // one CTA per item (A/B reference)
             } else {
-                const int ipc = lk_potrf_warp_items_per_cta();
-                lk_potrf_warp_kernel<<<(nb + ipc - 1) / ipc, 32 * ipc, lk_potrf_warp_smem_bytes(), st>>>(pp);
+                // up to 7 GPs per CTA (one warp each); small batches are spread over the SMs instead
+                const int ipc_max = lk_potrf_warp_items_per_cta();
+                int ipc = (nb + ctx->sm_count - 1) / ctx->sm_count;
+                ipc = ipc < 1 ? 1 : (ipc > ipc_max ? ipc_max : ipc);
+                lk_potrf_warp_kernel<<<(nb + ipc - 1) / ipc, 32 * ipc, lk_potrf_warp_smem_bytes() / ipc_max * ipc, st>>>(pp);
             }
             mark(1);
             ctx->launches++;

@@ -240,13 +240,13 @@ __device__ __forceinline__ int pw_w(int i, int k) { return (16 + i) * TS + ((k +
 __device__ __forceinline__ int pw_y(int m) { return (32 + (m >> 4)) * TS + (m & 15); }
 __device__ __forceinline__ int pw_piv(int m) { return (36 + (m >> 4)) * TS + (m & 15); }
 __device__ __forceinline__ int pw_rs(int c) { return 40 * TS + c; }
-size_t lk_potrf_warp_smem_bytes() { return sizeof(PotrfWarpSmem) * PW_WARPS; }
+size_t lk_potrf_warp_smem_bytes() { return sizeof(PotrfWarpSmem) * PW_WARPS; }  // per GP: / PW_WARPS
 int lk_potrf_warp_items_per_cta() { return PW_WARPS; }
 
 __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * PW_WARPS + warp;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;  // the launch decides how many GPs share a CTA (<= PW_WARPS)
     if (b >= prm.B) return;  // whole warp
     PotrfWarpSmem &sm = reinterpret_cast<PotrfWarpSmem *>(smem_raw)[warp];
     const int nt = prm.nt, j = prm.j, g = lane >> 2, t = lane & 3;
