@@ -374,7 +374,8 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_panel, cudaStreamNonBlocking, hi));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, lo));
         CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)big_col_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
@@ -403,7 +404,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaMemsetAsync(prm.flags + P, 1, sizeof(int), ctx->s_panel));  // panel_ready[P]
         for (int j = k0; j < j1 && j + 1 < nt; ++j) {
             prm.j = j;
-            big_col_flag_kernel<<<nt - j - 1, NTHREADS, smem, ctx->s_panel>>>(prm);
+            big_col_flag_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
             ctx->launches++;
         }
         return (int)GPL_OK;

@@ -34,9 +34,18 @@ struct __align__(16) BigSmem {
     double L16s[256];
 };
 
+// the column kernel of the worker protocol: two tile buffers are enough (74 KiB and <= 128 registers, so that three CTAs
+// of the trailing update still fit next to a waiting column CTA; with the 106 KiB layout only two did)
+struct __align__(16) ColSmem {
+    double A[TILE_ELEMS];
+    double Bt[TILE_ELEMS];
+    double D[DSIZE];
+    double ybuf[TS];
+};
 }  // namespace
 
 size_t big_smem_bytes() { return sizeof(BigSmem); }
+size_t big_col_smem_bytes() { return sizeof(ColSmem); }
 
 __global__ void __launch_bounds__(NTHREADS) dense_to_tiles_kernel(const double *__restrict__ A, int n, int nt,
                                                                   double *__restrict__ tiles) {
@@ -265,9 +274,9 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
 #endif
 }
 
-__global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    ColSmem &sm = *reinterpret_cast<ColSmem *>(smem_raw);
     const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
     int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
@@ -291,12 +300,13 @@ __global__ void __launch_bounds__(NTHREADS) big_col_flag_kernel(BigParams prm) {
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
     wait_flag_ge(diagdone + j, 1, tid);  // L_jj, its block inverses and z_j are stored
-    tile_load_async(sm.W, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
+    __syncthreads();  // the last update's operands are consumed: Bt takes L_jj
+    tile_load_async(sm.Bt, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
     block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    tile_trsm_ld(acc, sm.W, sm.D, tm);
+    tile_trsm_ld(acc, sm.Bt, sm.D, tm);
     acc_to_tile(Tij, acc, tm);
     if (prm.y) {
         __syncthreads();

@@ -116,6 +116,7 @@ __global__ void big_worker_kernel(BigParams prm);    // 1 CTA for the whole fact
 __global__ void big_col_flag_kernel(BigParams prm);
 __global__ void big_winv_kernel(BigParams prm);  // grid nt: W_jj = L_jj^-1 from L_jj and its block inverses  // nt - j - 1 CTAs; spins on diagdone[j], publishes rowdone[i]
 size_t big_smem_bytes();
+size_t big_col_smem_bytes();
 size_t big_trail_smem_bytes();
 
 // backward substitution alpha = L^-T z, one launch per tile row i (descending), grid = i + 1 CTAs; r = z on entry

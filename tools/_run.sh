@@ -1,5 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -2
-timeout 600 python tools/bench_configs.py 2>/dev/null | python -c "
-import json,sys; d=json.load(sys.stdin)
-for k,v in d.items(): print(k, {a: round(b,3) for a,b in v.items()})"
-timeout 300 python tools/sweep_small.py 2>&1 | grep "n=  512"
+timeout 60 python tools/run_c5.py 8192 3 2>&1 | tail -2
+timeout 60 python tools/run_c5.py 4096 2 2>&1 | tail -1
+timeout 60 python tools/run_c5.py 2048 2 2>&1 | tail -1
+timeout 400 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -2
