@@ -61,6 +61,35 @@ def test_lml_single_matches_oracle(ctx, n):
     assert abs(lml[0] - ref) <= LML_RTOL * abs(ref)
 
 
+@pytest.mark.parametrize("n,B", [(1100, 3), (1300, 2)])
+def test_lml_batched_beyond_the_shared_memory_z_window(ctx, n, B):
+    """n > 1088: the diagonal phase reads z from the global workspace instead of its shared-memory copy, and the
+    factor workspace of the lockstep schedule spans > 17 tile columns."""
+    X, y = _data(n, seed=70 + n)
+    prog = ctx.program(ALL_KINDS)
+    Th = np.vstack([THETA * (1.0 + 0.05 * b) for b in range(B)])
+    lml, info = ctx.lml_batched(prog, X, y, Th, 0.1)
+    for b in range(B):
+        ref, rinfo = CO.lml(ALL_KINDS, X, y, Th[b], 0.1)
+        assert info[b] == 0 and rinfo == 0
+        assert abs(lml[b] - ref) <= LML_RTOL * abs(ref)
+    lml_g, info_g, dth, dy = ctx.lml_batched(prog, X, y, Th[:1], 0.1, grad=True)   # fused gradient kernel, same n
+    assert abs(lml_g[0] - lml[0]) <= LML_RTOL * abs(lml[0])
+
+
+def test_lml_batched_workspace_chunking_is_invisible(ctx):
+    """A batch whose factor workspace exceeds the cap runs in chunks: same bits as in one piece."""
+    d = W.make_c3(features=300)
+    prog = ctx.program(d["ops"])
+    whole, info = ctx.lml_batched(prog, d["X"], d["Y"], d["Theta"], 0.0)
+    ctx.set_option("lk_ws_limit_mb", 24)          # 15 tiles x 32 KiB per item: ~50 items per chunk
+    try:
+        parts, info2 = ctx.lml_batched(prog, d["X"], d["Y"], d["Theta"], 0.0)
+    finally:
+        ctx.set_option("lk_ws_limit_mb", 12 * 1024)
+    assert np.array_equal(whole, parts) and np.array_equal(info, info2)
+
+
 def test_lml_c1_readme_shape(ctx):
     d = W.make_c1()
     prog = ctx.program(d["ops"])
