@@ -1,4 +1,4 @@
-timeout 60 python tools/run_c5.py 8192 3 2>&1 | tail -2
-timeout 60 python tools/run_c5.py 4096 2 2>&1 | tail -1
-timeout 60 python tools/run_c5.py 2048 2 2>&1 | tail -1
-timeout 400 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -2
+set -x
+CHOLV=3 timeout 300 python tools/run_c5.py 8192 1 > gpurun_out/c5_v3.log 2>&1 || exit 1
+CHOLV=3 timeout 900 ncu --set full --clock-control none --import-source on -k regex:big_trail -s 3 -c 1 -o gpurun_out/trail2 -f python tools/run_c5.py 8192 1 > gpurun_out/ncu.log 2>&1
+ls -la gpurun_out/trail2.ncu-rep
