@@ -902,12 +902,27 @@ int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean
     bool &attr_set = ctx->attr_pred;
     if (!attr_set) {
         CU(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(predict_kernel_nb6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(predict_kernel_nb4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int occ = 0;
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, predict_kernel, NTHREADS, smem));
     if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "predict kernel does not fit on an SM");
-    const int nslab = (m + TS - 1) / TS;
+    // slab width (64, 48 or 32 test points): the one whose busiest SM has the fewest points (ties: the wider)
+    int nb_blocks = 8;
+    {
+        long long best = -1;
+        for (int nb : {8, 6, 4}) {
+            const long long ns = (m + 8 * nb - 1) / (8 * nb);
+            const long long cost = ((ns + ctx->sm_count - 1) / ctx->sm_count) * nb;
+            if (best < 0 || cost < best) {
+                best = cost;
+                nb_blocks = nb;
+            }
+        }
+    }
+    const int nslab = (m + 8 * nb_blocks - 1) / (8 * nb_blocks);
     int grid = ctx->sm_count * occ;
     if (grid > nslab) grid = nslab;
     int rc;
@@ -932,7 +947,9 @@ int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean
     prm.wsV = ptr<double>(ctx->bWsV);
     prm.mean = ptr<double>(ctx->bMean);
     prm.var = ptr<double>(ctx->bVar);
-    predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    if (nb_blocks == 8) predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    else if (nb_blocks == 6) predict_kernel_nb6<<<grid, NTHREADS, smem, st>>>(prm);
+    else predict_kernel_nb4<<<grid, NTHREADS, smem, st>>>(prm);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(mean, ctx->bMean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));

@@ -135,7 +135,9 @@ struct PredictParams {
     double *wsV;          // per-CTA workspace, nt tiles
     double *mean, *var;
 };
-__global__ void predict_kernel(const __grid_constant__ PredictParams prm);
+__global__ void predict_kernel(const __grid_constant__ PredictParams prm);      // slabs of 64 test points
+__global__ void predict_kernel_nb6(const __grid_constant__ PredictParams prm);  // 48
+__global__ void predict_kernel_nb4(const __grid_constant__ PredictParams prm);  // 32
 size_t predict_smem_bytes();
 
 // out (n x S) = L Z

@@ -23,7 +23,11 @@ struct __align__(16) PredSmem {
 
 size_t predict_smem_bytes() { return sizeof(PredSmem); }
 
-__global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_constant__ PredictParams prm) {
+// NB: 8-column blocks of test points per slab (slab width 8 NB <= 64).  The host picks the width that balances the slabs
+// over the SMs (20 000 points: 313 slabs of 64 put three slabs on 17 SMs and two on the rest; 417 slabs of 48 finish
+// ~20 % sooner although each DMMA step feeds six n-blocks instead of eight).
+template <int NB>
+__device__ __forceinline__ void predict_body(const PredictParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PredSmem &sm = *reinterpret_cast<PredSmem *>(smem_raw);
     const DevProgram &P = prm.prog;
@@ -35,11 +39,13 @@ __global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_const
     prepare_item_scalars(P, prm.theta, &sm.sc, tid);
     __syncthreads();
 
-    const int nslab = (m + TS - 1) / TS;
+    constexpr int WS = 8 * NB, MASK = (1 << NB) - 1;  // slab width, active n-blocks
+    static_assert(NB % 2 == 0 && NB >= 2 && NB <= 8, "whole 16-column quarters");
+    const int nslab = (m + WS - 1) / WS;
     for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
         int gj[NCC];
 #pragma unroll
-        for (int cc = 0; cc < NCC; ++cc) gj[cc] = s * TS + col_of(tm, cc);
+        for (int cc = 0; cc < NCC; ++cc) gj[cc] = s * WS + col_of(tm, cc);
         double csq[NCC], cmean[NCC];
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) csq[cc] = cmean[cc] = 0.0;
@@ -48,7 +54,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_const
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
             double acc[2][NCC];
-            eval_block_acc<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, s * TS, tm.t, 0.0, acc);
+            eval_block_acc<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, s * WS, tm.t, 0.0, acc, NB / 2);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
                 const double al = gi[mb] < n ? prm.alpha[gi[mb]] : 0.0;
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_const
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncthreads();
-                tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+                tile_mma<true, MASK>(acc, sm.A, sm.Bt, tm, 0, TS);
             }
             // V_i = W_ii acc  (W lower triangular: rows of this warp need k < r0 + 16)
             __syncthreads();
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_const
             cp_async_wait<0>();
             __syncthreads();
             acc_zero(acc);
-            tile_mma<false>(acc, sm.A, sm.Bt, tm, 0, tm.r0 + 16);
+            tile_mma<false, MASK>(acc, sm.A, sm.Bt, tm, 0, tm.r0 + 16);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
@@ -87,31 +93,35 @@ __global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_const
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) part[slot * TS + col_of(tm, cc)] = cmean[cc];
         __syncthreads();
-        if (tid < TS && s * TS + tid < m) {
+        if (tid < WS && s * WS + tid < m) {
             double sum = 0.0;
 #pragma unroll 8
             for (int gq = 0; gq < 32; ++gq) sum += part[gq * TS + tid];
-            prm.mean[s * TS + tid] = sum;
+            prm.mean[s * WS + tid] = sum;
         }
         if (prm.want_var) {
             __syncthreads();
 #pragma unroll
             for (int cc = 0; cc < NCC; ++cc) part[slot * TS + col_of(tm, cc)] = csq[cc];
             __syncthreads();
-            if (tid < TS && s * TS + tid < m) {
+            if (tid < WS && s * WS + tid < m) {
                 double sum = 0.0;
 #pragma unroll 8
                 for (int gq = 0; gq < 32; ++gq) sum += part[gq * TS + tid];
                 // prior variance of the latent function at x*: Noise contributes 0 (SAME = false)
-                int one_i[1] = {s * TS + tid}, one_j[1] = {s * TS + tid};
+                int one_i[1] = {s * WS + tid}, one_j[1] = {s * WS + tid};
                 double kss[1][1];
                 eval_block<1, 1, false>(P, sm.sc, prm.Xs, m, m, one_i, prm.Xs, m, m, one_j, 0.0, kss);
-                prm.var[s * TS + tid] = kss[0][0] - sum;
+                prm.var[s * WS + tid] = kss[0][0] - sum;
             }
         }
         __syncthreads();
     }
 }
+
+__global__ void __launch_bounds__(NTHREADS, 3) predict_kernel(const __grid_constant__ PredictParams prm) { predict_body<8>(prm); }
+__global__ void __launch_bounds__(NTHREADS, 3) predict_kernel_nb6(const __grid_constant__ PredictParams prm) { predict_body<6>(prm); }
+__global__ void __launch_bounds__(NTHREADS, 3) predict_kernel_nb4(const __grid_constant__ PredictParams prm) { predict_body<4>(prm); }
 
 // out (n x S) = L Z : grid = nt CTAs (tile row i), thread (row = tid % 64, sample lane = tid / 64: 2 samples at a time)
 __global__ void __launch_bounds__(NTHREADS) sample_kernel(const double *tiles, int nt, int n, const double *Z, int S,

@@ -230,6 +230,26 @@ def test_posterior_and_predict_match_oracle(ctx, n, variant):
     post.free()
 
 
+@pytest.mark.parametrize("m", [1, 33, 9472, 12000, 14000])
+def test_predict_every_slab_width(ctx, m):
+    """The host picks slabs of 64, 48 or 32 test points by SM balance (9472 -> 64, 12000 and 14000 -> 48, small -> 32):
+    all widths, ragged last slabs included, must agree with the oracle."""
+    X, y = _data(130, seed=5)
+    prog = ctx.program(ALL_KINDS)
+    post = ctx.posterior_fit(prog, X, y, THETA, 0.1)
+    rng = np.random.default_rng(m)
+    Xs = np.column_stack([rng.uniform(-3, 3, m), rng.uniform(0, 5, m), rng.standard_normal(m),
+                          rng.integers(0, 4, m).astype(float)])
+    mean, var = post.mean_and_var(Xs)
+    idx = np.unique(np.concatenate([np.arange(min(m, 70)), np.arange(max(0, m - 70), m), rng.integers(0, m, 100)]))
+    U, alpha = CO.posterior(ALL_KINDS, X, y, THETA, 0.1)
+    rm, rv = CO.mean_and_var(ALL_KINDS, X, U, alpha, np.ascontiguousarray(Xs[idx]), THETA)
+    assert np.max(np.abs(mean[idx] - rm)) < PRED_TOL * max(1.0, np.max(np.abs(rm)))
+    assert np.max(np.abs(var[idx] - rv)) < PRED_TOL * max(1.0, np.max(np.abs(rv)))
+    assert np.all(np.isfinite(mean)) and np.all(np.isfinite(var))
+    post.free()
+
+
 def test_posterior_plot_call_sequence(ctx):
     """src/plotting.jl:6-12: FiniteGP(gp, x, 0.1) -> posterior -> mean_and_var at 100 grid points."""
     import gaplac_b200 as G
