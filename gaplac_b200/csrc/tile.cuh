@@ -146,6 +146,10 @@ __device__ __forceinline__ void acc_from_tile(double (&acc)[2][NCC], const doubl
         for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = T[tidx(row_of(tm, mb), col_of(tm, cc))];
 }
 
+#ifndef GPL_MMA_UNROLL
+#define GPL_MMA_UNROLL 4
+#endif
+constexpr int MMA_UNROLL = GPL_MMA_UNROLL;  // k4-steps unrolled in tile_mma
 // ---- GEMM core on the FP64 tensor-core path ------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -166,7 +170,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][NCC], const double *__
     const double *pa1 = A + tm.t * TS + ((tm.r0 + 8 + tm.g) ^ sw);
     const double *pbe = B + tm.t * TS + (tm.g ^ (sw & 4)) + (sw & 8);        // even n-blocks
     const double *pbo = B + tm.t * TS + (tm.g ^ (sw & 4)) + (8 ^ (sw & 8));  // odd n-blocks
-#pragma unroll 2
+#pragma unroll MMA_UNROLL
     for (int k = k0; k < k1; k += 4) {
         double a0 = pa0[k * TS], a1 = pa1[k * TS];
         if (SUB) {
