@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
 // trailing kernels around it.  Synchronisation is through three flag arrays in global memory:
 //   panel_ready[P]  set by the host (stream-ordered memset) once every earlier panel's update of panel P's columns is done
 //   rowdone[i]      = j + 1 once tile (i, j) is final and y_i carries column j   (written by big_col_flag_kernel)
-//   diagdone[j]     != 0 once L_jj, W_jj and z_j are stored                      (written by the worker)
+//   diagdone[j]     1 once L_jj and its block inverses are stored, 2 once z_j is   (written by the worker)
 __device__ __forceinline__ int ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void wait_flag_ge(const int *p, int v, int tid) {
     if (tid == 0) {
@@ -257,17 +257,19 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         // off this serial path.
         acc_to_tile(Tjj, acc, tm);
         for (int t = tid; t < DSIZE; t += NTHREADS) prm.dblk[(size_t)j * DSIZE + t] = sm.D[t];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;  // the solves below the tile can start
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
-        if (prm.y) {
-            __syncthreads();
+        if (prm.y) {  // z_j while the column CTAs load L_jj and solve: they need it only for their right-hand sides
             acc_to_tile(sm.A, acc, tm);
             if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
             tile_forward_solve(sm.A, sm.D, sm.ybuf, sm.rsbuf, tid);  // z_j = L_jj^-1 y_j
             if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 2;  // ... and z_j is stored
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;
     }
 #ifdef GPL_BIG_PROFILE
     if (tid == 0) printf("worker: total %lld clk, waiting for panel_ready %lld, for rowdone %lld, working %lld\n", clock64() - t_begin, t_wait_panel, t_wait_row, clock64() - t_begin - t_wait_panel - t_wait_row);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
         __syncthreads();
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
-    wait_flag_ge(diagdone + j, 1, tid);  // L_jj, its block inverses and z_j are stored
+    wait_flag_ge(diagdone + j, 1, tid);  // L_jj and its block inverses are stored
     __syncthreads();  // the last update's operands are consumed: Bt takes L_jj
     tile_load_async(sm.Bt, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
     block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
@@ -311,6 +313,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
     if (prm.y) {
         __syncthreads();
         acc_to_tile(sm.A, acc, tm);
+        wait_flag_ge(diagdone + j, 2, tid);  // z_j (published after L_jj; normally long since)
         if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
         __syncthreads();
         if (tid < TS) prm.y[i * TS + tid] = __ldcg(prm.y + i * TS + tid) - tile_row_dot(sm.A, sm.ybuf, tid, 0, TS);
