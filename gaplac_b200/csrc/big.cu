@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
     int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
     constexpr int PANEL_ = BIG_PANEL;
 #ifdef GPL_BIG_PROFILE
-    long long t_wait_panel = 0, t_wait_row = 0, t_begin = clock64();
+    long long t_wait_panel = 0, t_wait_row = 0, t_begin = clock64(), t_pre = 0, t_last = 0, t_potrf = 0, t_pub = 0, t_fwd = 0;
 #endif
     for (int j = 0; j < nt; ++j) {
         const int k0 = (j / PANEL_) * PANEL_;
@@ -235,10 +235,12 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         }
 #ifdef GPL_BIG_PROFILE
         long long tc = clock64();
+        t_pre += tc - tb;
 #endif
         if (j > 0) wait_flag_ge(rowdone + j, j, tid);
 #ifdef GPL_BIG_PROFILE
-        t_wait_row += clock64() - tc;
+        long long td = clock64();
+        t_wait_row += td - tc;
 #endif
         if (j > k0) {  // the last term: tile (j, j-1)
             double *cur = ((j - 1 - k0) & 1) ? sm.A : sm.Bt;
@@ -250,7 +252,15 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
             tile_mma<true>(acc, cur, cur, tm, 0, TS);
         }
         __syncthreads();
+#ifdef GPL_BIG_PROFILE
+        long long te = clock64();
+        t_last += te - td;
+#endif
         const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+#ifdef GPL_BIG_PROFILE
+        long long tf = clock64();
+        t_potrf += tf - te;
+#endif
         if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
         // Publish L_jj and the inverses of its 16 x 16 diagonal blocks; that is all the column kernel needs for its solve.
         // The full inverse W_jj (backward substitution, posterior) is formed after the factorisation by big_winv_kernel,
@@ -260,6 +270,10 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         __threadfence();
         __syncthreads();
         if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;  // the solves below the tile can start
+#ifdef GPL_BIG_PROFILE
+        long long tg = clock64();
+        t_pub += tg - tf;
+#endif
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
         if (prm.y) {  // z_j while the column CTAs load L_jj and solve: they need it only for their right-hand sides
             acc_to_tile(sm.A, acc, tm);
@@ -270,9 +284,16 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
             __syncthreads();
             if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 2;  // ... and z_j is stored
         }
+#ifdef GPL_BIG_PROFILE
+        t_fwd += clock64() - tg;
+#endif
     }
 #ifdef GPL_BIG_PROFILE
-    if (tid == 0) printf("worker: total %lld clk, waiting for panel_ready %lld, for rowdone %lld, working %lld\n", clock64() - t_begin, t_wait_panel, t_wait_row, clock64() - t_begin - t_wait_panel - t_wait_row);
+    if (tid == 0)
+        printf("worker: total %lld clk, waiting for panel_ready %lld, for rowdone %lld, working %lld (load + early updates %lld, "
+               "last update %lld, potrf %lld, publish %lld, pivlog + forward solve %lld)\n",
+               clock64() - t_begin, t_wait_panel, t_wait_row, clock64() - t_begin - t_wait_panel - t_wait_row, t_pre, t_last,
+               t_potrf, t_pub, t_fwd);
 #endif
 }
 
