@@ -379,12 +379,13 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
-    int rc = ensure(ctx, ctx->bigFlags, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int));
+    const size_t nflags = (size_t)BIG_MAXP + 3 * (size_t)nt;
+    int rc = ensure(ctx, ctx->bigFlags, nflags * sizeof(int));
     if (rc) return rc;
     prm.flags = ptr<int>(ctx->bigFlags);
     if ((rc = ensure(ctx, ctx->bigD, (size_t)nt * DSIZE * sizeof(double)))) return rc;
     prm.dblk = ptr<double>(ctx->bigD);
-    CU(ctx, cudaMemsetAsync(prm.flags, 0, (size_t)(BIG_MAXP + 2 * nt) * sizeof(int), st));
+    CU(ctx, cudaMemsetAsync(prm.flags, 0, nflags * sizeof(int), st));
     const size_t diag_smem = 200 * 1024;
     std::vector<cudaEvent_t> eF(NP), eB(NP);
     for (int P = 0; P < NP; ++P) {

@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
 // share its sub-partitions and starve its pivot chains, tools/pipe_mix.cu), while the host streams the column and
 // trailing kernels around it.  Synchronisation is through three flag arrays in global memory:
 //   panel_ready[P]  set by the host (stream-ordered memset) once every earlier panel's update of panel P's columns is done
-//   rowdone[i]      = j + 1 once tile (i, j) is final and y_i carries column j   (written by big_col_flag_kernel)
+//   tiledone[i]     = j + 1 once tile (i, j) is final                            (written by big_col_flag_kernel)
+//   rowdone[i]      = j + 1 once, in addition, y_i carries column j              (written by big_col_flag_kernel)
 //   diagdone[j]     1 once L_jj and its block inverses are stored, 2 once z_j is   (written by the worker)
 __device__ __forceinline__ int ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void wait_flag_ge(const int *p, int v, int tid) {
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
     BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
     const int tid = threadIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
-    int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
+    int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
     constexpr int PANEL_ = BIG_PANEL;
 #ifdef GPL_BIG_PROFILE
     long long t_wait_panel = 0, t_wait_row = 0, t_begin = clock64(), t_pre = 0, t_last = 0, t_potrf = 0, t_pub = 0, t_fwd = 0;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         // on the serial path.
         double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
         double acc[2][NCC];
-        if (j - k0 >= 2) wait_flag_ge(rowdone + j, j - 1, tid);  // tiles (j, k0..j-2) are final (normally long since)
+        if (j - k0 >= 2) wait_flag_ge(tiledone + j, j - 1, tid);  // tiles (j, k0..j-2) are final (normally long since)
         __syncthreads();
         tile_load_async(sm.A, Tjj, tid);
         cp_async_commit();
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         long long tc = clock64();
         t_pre += tc - tb;
 #endif
-        if (j > 0) wait_flag_ge(rowdone + j, j, tid);
+        if (j > 0) wait_flag_ge(tiledone + j, j, tid);
 #ifdef GPL_BIG_PROFILE
         long long td = clock64();
         t_wait_row += td - tc;
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
         if (prm.y) {  // z_j while the column CTAs load L_jj and solve: they need it only for their right-hand sides
             acc_to_tile(sm.A, acc, tm);
+            if (j > 0) wait_flag_ge(rowdone + j, j, tid);  // y_j carries every earlier column (set after tiledone)
             if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
             tile_forward_solve(sm.A, sm.D, sm.ybuf, sm.rsbuf, tid);  // z_j = L_jj^-1 y_j
             if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
     ColSmem &sm = *reinterpret_cast<ColSmem *>(smem_raw);
     const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
-    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt;
+    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
     double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
     // the tile itself receives no further outside update: fetch it while the worker is still on the diagonal tile
     tile_load_async(sm.A, Tij, tid);
@@ -331,8 +333,10 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
     __syncthreads();
     tile_trsm_ld(acc, sm.Bt, sm.D, tm);
     acc_to_tile(Tij, acc, tm);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int *>(tiledone + i) = j + 1;  // the worker's next update needs only the tile
     if (prm.y) {
-        __syncthreads();
         acc_to_tile(sm.A, acc, tm);
         wait_flag_ge(diagdone + j, 2, tid);  // z_j (published after L_jj; normally long since)
         if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
