@@ -1,0 +1,75 @@
+"""Chain-averaged predictions and chain evidence: host summaries on CPU, the per-row
+posteriors against the oracle on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import gaplac_b200 as G
+from gaplac_b200.formula import KernelProgram
+from oracle import c_oracle as CO
+from oracle import gp_oracle as O
+
+
+def test_mixture_summary_matches_root_finding():
+    from scipy.optimize import brentq
+    from scipy.special import ndtr
+
+    rng = np.random.default_rng(1)
+    mu = rng.normal(0, 2, (9, 6))
+    var = rng.uniform(0.01, 3, (9, 6))
+    var[:, 5] = 0.0                       # degenerate components: a mixture of point masses
+    qs = (0.05, 0.25, 0.5, 0.95)
+    mean, sd, Q = G.mixture_summary(mu, var, qs)
+    assert np.allclose(mean, mu.mean(0), rtol=0, atol=1e-15)
+    assert np.allclose(sd ** 2, (var + mu ** 2).mean(0) - mu.mean(0) ** 2, rtol=1e-12, atol=1e-14)
+    for c in range(5):
+        for qi, q in enumerate(qs):
+            f = lambda x: ndtr((x - mu[:, c]) / np.sqrt(var[:, c])).mean() - q
+            ref = brentq(f, mu[:, c].min() - 20, mu[:, c].max() + 20, xtol=1e-14, rtol=1e-15)
+            assert abs(Q[qi, c] - ref) < 1e-10
+    srt = np.sort(mu[:, 5])               # point masses: the quantile is an order statistic
+    assert abs(Q[2, 5] - srt[4]) < 1e-9   # median of 9 atoms
+
+
+def test_single_component_quantiles_are_gaussian():
+    from scipy.special import ndtri
+    mean, sd, Q = G.mixture_summary([[1.5, -2.0]], [[4.0, 0.25]], (0.05, 0.95))
+    assert np.allclose(Q[0], np.array([1.5, -2.0]) + ndtri(0.05) * np.array([2.0, 0.5]), atol=1e-12)
+    assert np.allclose(Q[1], np.array([1.5, -2.0]) + ndtri(0.95) * np.array([2.0, 0.5]), atol=1e-12)
+
+
+def test_harmonic_evidence_is_stable_where_the_naive_form_overflows():
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 60
+    ll = np.array([-939.2, -941.7, -938.8, -945.1, -940.0])       # the golden chains live here: exp(939) overflows
+    ref = mp.log(len(ll) / sum(mp.exp(-mp.mpf(float(v))) for v in ll))
+    assert abs(G.log_evidence_harmonic(ll) - float(ref)) < 1e-12 * abs(float(ref))
+    ll2 = ll - 3.0
+    assert abs(G.log_bayes_factor(ll, ll2) - 3.0 / np.log(10.0)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_predict_chain_golden_model_matches_oracle():
+    """`predict ... --mcmc mcmc_3206.tsv --at "nutrient=-5:0.5:5;PersonID=0;StoolPairs=0"` (test/pred.jl:22): per-row
+    posterior mean / variance against the oracle, mixture columns from the same host summary."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    X, y, Th, s2, lpi, prior = O.load_golden("3206", gdir)
+    ops = O.golden_program("3206")
+    rows = [0, 17, 50, 99]
+    nut = np.arange(-5.0, 5.0001, 0.5)
+    Xs = np.column_stack([np.zeros_like(nut), np.zeros_like(nut), nut])
+    gp = G.GP(KernelProgram(ops=ops, vars=["PersonID", "StoolPairs", "nutrient"], n_theta=4))
+    out = G.predict_chain(gp, X, y, Th[rows], Xs, sigma2=0.0, jitter=1e-9, obs_var=Th[rows, 3])
+    mu = np.empty((len(rows), len(nut)))
+    var = np.empty_like(mu)
+    for k, r in enumerate(rows):
+        U, alpha = CO.posterior(ops, X, y, Th[r], 0.0, jitter=1e-9)
+        mu[k], var[k] = CO.mean_and_var(ops, X, U, alpha, Xs, Th[r])
+    assert np.max(np.abs(out["mu"] - mu)) < 1e-8 * max(1.0, np.max(np.abs(mu)))
+    assert np.max(np.abs(out["var"] - var)) < 1e-8 * max(1.0, np.max(np.abs(var)))
+    fm, fs, fQ = G.mixture_summary(mu, var, (0.05, 0.5, 0.95))
+    ym, ys, yQ = G.mixture_summary(mu, var + Th[rows, 3][:, None], (0.05, 0.5, 0.95))
+    assert np.allclose(out["fmu"], fm, atol=1e-8) and np.allclose(out["ymu"], ym, atol=1e-8)
+    assert np.allclose(out["yQ050"], yQ[0], atol=1e-7) and np.allclose(out["yQ950"], yQ[2], atol=1e-7)
+    assert np.all(out["yQ950"] - out["yQ050"] > out["fQ950"] - out["fQ050"])   # observation noise widens the band
