@@ -24,6 +24,7 @@ SYMBOLS = [
     "gpl_cov", "gpl_cov_dev", "gpl_cross_cov", "gpl_lml_batched", "gpl_lml_batched_dev", "gpl_posterior_fit",
     "gpl_posterior_free", "gpl_posterior_logpdf", "gpl_posterior_alpha", "gpl_posterior_factor",
     "gpl_posterior_mean_var", "gpl_sample", "gpl_chol_logdet", "gpl_chol_logdet_dev", "gpl_lml_large",
+    "gpl_predict_batched",
 ]
 
 
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
     lib.gpl_posterior_alpha.argtypes = [_vp, _vp]
     lib.gpl_posterior_factor.argtypes = [_vp, _vp]
     lib.gpl_posterior_mean_var.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
+    lib.gpl_predict_batched.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double,
+                                        C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
     lib.gpl_sample.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, C.c_int, _vp]
     lib.gpl_chol_logdet.argtypes = [_vp, C.c_int, _vp, C.c_int, _dp, _ip]
     lib.gpl_chol_logdet_dev.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
@@ -300,6 +303,30 @@ class Context:
         _check(self.h, load().gpl_posterior_fit(self.h, prog.h, n, d, _ptr(X), _ptr(y), _ptr(th), th.size, sigma2,
                                                 jitter, C.byref(h)))
         return Posterior(self, h, n, d)
+
+    def predict_batched(self, prog: Program, X, y, Theta, sigma2, Xs, jitter: float = 0.0, want_var: bool = True):
+        """One posterior per row of Theta (B, p) over shared (X, y); predictions at Xs (m, d).
+        Returns (mean[B, m], var[B, m] or None, lml[B], info[B])."""
+        X = _fa(X, 2)
+        n, d = X.shape
+        y = _fa(y)
+        Theta = np.ascontiguousarray(np.atleast_2d(np.asarray(Theta, dtype=np.float64)))  # (B, p) C-order == p x B col-major
+        B, p = Theta.shape
+        s2 = np.ascontiguousarray(np.atleast_1d(np.asarray(sigma2, dtype=np.float64)))
+        if s2.size not in (1, B):
+            raise ValueError("sigma2 must be a scalar or have one value per row of Theta")
+        Xs = _fa(Xs, 2)
+        m = Xs.shape[0]
+        if Xs.shape[1] != d:
+            raise ValueError("Xs must have the same number of columns as X")
+        mean = np.empty((B, m))
+        var = np.empty((B, m)) if want_var else None
+        lml = np.empty(B)
+        info = np.zeros(B, dtype=np.int32)
+        _check(self.h, load().gpl_predict_batched(self.h, prog.h, n, d, _ptr(X), _ptr(y), _ptr(Theta), p, _ptr(s2),
+                                                  int(s2.size == B and B > 1), jitter, B, m, _ptr(Xs), _ptr(mean),
+                                                  _ptr(var) if want_var else None, _ptr(lml), _ptr(info)))
+        return mean, var, lml, info
 
     def sample(self, prog: Program, X, theta, sigma2: float, Z, jitter: float = 0.0) -> np.ndarray:
         X = _fa(X, 2)

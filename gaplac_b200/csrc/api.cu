@@ -39,7 +39,7 @@ struct gpl_ctx {
     char name[128] = {0};
     cudaStream_t stream = nullptr;
     cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
-    DevBuf bigFlags, bigD;
+    DevBuf bigFlags, bigD, lkW, lkAlpha;
     std::vector<std::pair<void *, size_t>> postFree;  // device blocks of freed posteriors (cudaMalloc / cudaFree cost
                                                       // milliseconds next to multi-GB workspaces: a refit reuses them)
     uint64_t launches = 0;
@@ -47,7 +47,7 @@ struct gpl_ctx {
     std::mutex mu;
     int lml_variant = 0;
     int chol_variant = 0;
-    bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false;
+    bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
     size_t lk_ws_limit = (size_t)12 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[3] = {0, 0, 0};            // last instrumented call: total ms in diag / potrf / below kernels
@@ -528,7 +528,7 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
@@ -939,6 +939,9 @@ int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean
     prm.p = post->p;
     prm.m = m;
     prm.want_var = var != nullptr;
+    prm.items = 0;
+    prm.theta_stride = prm.tiles_stride = prm.winv_stride = prm.alpha_stride = 0;
+    prm.info = nullptr;
     prm.X = post->dX;
     prm.theta = post->dtheta;
     prm.Xs = ptr<double>(ctx->bXs);
@@ -955,6 +958,116 @@ int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(mean, ctx->bMean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
     if (var) CU(ctx, cudaMemcpyAsync(var, ctx->bVar.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GPL_OK;
+}
+
+// ---- batched posteriors + predictions over the rows of an MCMC chain -------------------------------------------------
+// Replaces, for every chain row b at once,  post_b = posterior(FiniteGP(GP(kernel(theta_b)), X, sigma2_b), y);
+// mean_and_var(post_b, Xs)  - the loop behind the `predict` / `fitplot` commands (CLI/src/main.jl:8-16, output columns
+// test/pred.jl:11-14) and src/plotting.jl:6-12.  All rows are factored by the lockstep schedule in one go; lk_post_kernel
+// forms the diagonal-tile inverses and alpha per row; the prediction kernel runs over (row, slab of test points) pairs.
+int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                        const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter, int B, int m,
+                        const double *Xs, double *mean, double *var, double *lml, int *info) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (B <= 0 || m <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_predict_batched: B=%d m=%d", B, m);
+    if (!X || !y || !sigma2 || !Xs || !mean || (p > 0 && !Theta)) return fail(ctx, GPL_ERR_ARG, "gpl_predict_batched: null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nt = (n + TS - 1) / TS;
+    const long long ntri = tri_index(nt, 0);
+    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16;
+    if (per_item * (size_t)B > ctx->lk_ws_limit)
+        return fail(ctx, GPL_ERR_LIMIT, "gpl_predict_batched: %d rows of n=%d exceed the factor workspace cap; split the chain", B, n);
+    const size_t tb = (size_t)(p > 0 ? p : 1) * B * 8, sb = (size_t)(sigma2_batched ? B : 1) * 8;
+    if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bY, (size_t)n * 8)) ||
+        (rc = ensure(ctx, ctx->bTheta, tb)) || (rc = ensure(ctx, ctx->bSigma, sb)) || (rc = ensure(ctx, ctx->bLml, (size_t)B * 8)) ||
+        (rc = ensure(ctx, ctx->bInfo, (size_t)B * 4)) || (rc = ensure(ctx, ctx->bXs, (size_t)m * d * 8)) ||
+        (rc = ensure(ctx, ctx->bMean, (size_t)m * B * 8)) || (rc = ensure(ctx, ctx->bVar, (size_t)m * B * 8)) ||
+        (rc = ensure(ctx, ctx->lkW, (size_t)B * nt * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkAlpha, (size_t)B * nt * TS * 8)))
+        return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bY.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, Theta, (size_t)p * B * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bSigma.p, sigma2, sb, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->bXs.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_lml_lockstep(ctx, prog->dev, n, d, ptr<double>(ctx->bX), 0, ptr<double>(ctx->bY), 0, ptr<double>(ctx->bTheta), p,
+                             ptr<double>(ctx->bSigma), sigma2_batched, jitter, B, ptr<double>(ctx->bLml), ptr<int>(ctx->bInfo), st);
+    if (rc) return rc;
+    if (!ctx->attr_post) {
+        CU(ctx, cudaFuncSetAttribute(lk_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_post_smem_bytes()));
+        ctx->attr_post = true;
+    }
+    LkPostParams pq;
+    pq.nt = nt;
+    pq.tiles = ptr<double>(ctx->lkTiles);
+    pq.dblk = ptr<double>(ctx->lkD);
+    pq.z = ptr<double>(ctx->lkZ);
+    pq.winv = ptr<double>(ctx->lkW);
+    pq.alpha = ptr<double>(ctx->lkAlpha);
+    lk_post_kernel<<<B, NTHREADS, lk_post_smem_bytes(), st>>>(pq);
+    ctx->launches++;
+    const size_t smem = predict_smem_bytes();
+    if (!ctx->attr_pred) {
+        CU(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(predict_kernel_nb6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(ctx, cudaFuncSetAttribute(predict_kernel_nb4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->attr_pred = true;
+    }
+    int occ = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, predict_kernel, NTHREADS, smem));
+    if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "predict kernel does not fit on an SM");
+    int nb_blocks = 8;
+    {
+        long long best = -1;
+        for (int nb : {8, 6, 4}) {
+            const long long units = (long long)B * ((m + 8 * nb - 1) / (8 * nb));
+            const long long cost = ((units + ctx->sm_count - 1) / ctx->sm_count) * nb;
+            if (best < 0 || cost < best) {
+                best = cost;
+                nb_blocks = nb;
+            }
+        }
+    }
+    const long long units = (long long)B * ((m + 8 * nb_blocks - 1) / (8 * nb_blocks));
+    int grid = ctx->sm_count * occ;
+    if (grid > units) grid = (int)units;
+    if ((rc = ensure(ctx, ctx->bWsV, (size_t)grid * nt * TILE_BYTES))) return rc;
+    PredictParams prm;
+    prm.prog = prog->dev;
+    prm.n = n;
+    prm.nt = nt;
+    prm.d = d;
+    prm.p = p;
+    prm.m = m;
+    prm.want_var = var != nullptr;
+    prm.items = B;
+    prm.theta_stride = p;
+    prm.tiles_stride = ntri * TILE_ELEMS;
+    prm.winv_stride = (long long)nt * TILE_ELEMS;
+    prm.alpha_stride = (long long)nt * TS;
+    prm.info = ptr<int>(ctx->bInfo);
+    prm.X = ptr<double>(ctx->bX);
+    prm.theta = ptr<double>(ctx->bTheta);
+    prm.Xs = ptr<double>(ctx->bXs);
+    prm.tiles = ptr<double>(ctx->lkTiles);
+    prm.winv = ptr<double>(ctx->lkW);
+    prm.alpha = ptr<double>(ctx->lkAlpha);
+    prm.wsV = ptr<double>(ctx->bWsV);
+    prm.mean = ptr<double>(ctx->bMean);
+    prm.var = ptr<double>(ctx->bVar);
+    if (nb_blocks == 8) predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    else if (nb_blocks == 6) predict_kernel_nb6<<<grid, NTHREADS, smem, st>>>(prm);
+    else predict_kernel_nb4<<<grid, NTHREADS, smem, st>>>(prm);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(mean, ctx->bMean.p, (size_t)m * B * 8, cudaMemcpyDeviceToHost, st));
+    if (var) CU(ctx, cudaMemcpyAsync(var, ctx->bVar.p, (size_t)m * B * 8, cudaMemcpyDeviceToHost, st));
+    if (lml) CU(ctx, cudaMemcpyAsync(lml, ctx->bLml.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (info) CU(ctx, cudaMemcpyAsync(info, ctx->bInfo.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return GPL_OK;
 }

@@ -134,7 +134,22 @@ struct PredictParams {
     const double *tiles, *winv, *alpha;
     double *wsV;          // per-CTA workspace, nt tiles
     double *mean, *var;
+    // batched form (several posteriors over the same X, e.g. the rows of an MCMC chain): item b reads theta, tiles, winv,
+    // alpha at b * stride and writes mean / var at b * m; `info` (optional) marks items whose factorisation failed
+    int items;            // 0 or 1: single posterior
+    long long theta_stride, tiles_stride, winv_stride, alpha_stride;
+    const int *info;
 };
+// Batched posteriors on top of the lockstep workspace: per item b the inverses of the diagonal tiles (from L_jj and its
+// block inverses) and alpha = L^-T z.  grid B.
+struct LkPostParams {
+    int nt;
+    const double *tiles, *dblk, *z;  // lockstep workspace: B x ntri tiles, B x nt x DSIZE, B x nt*64
+    double *winv;                    // B x nt tiles
+    double *alpha;                   // B x nt*64
+};
+__global__ void lk_post_kernel(const __grid_constant__ LkPostParams prm);
+size_t lk_post_smem_bytes();
 __global__ void predict_kernel(const __grid_constant__ PredictParams prm);      // slabs of 64 test points
 __global__ void predict_kernel_nb6(const __grid_constant__ PredictParams prm);  // 48
 __global__ void predict_kernel_nb4(const __grid_constant__ PredictParams prm);  // 32

@@ -536,4 +536,59 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     }
 }
 
+// ---- batched posteriors from the lockstep workspace ----------------------------------------------------------------
+// After the factorisation of B items (L tiles, block inverses and z = L^-1 y in the workspace) one CTA per item forms
+// what mean_and_var needs: the inverses of the diagonal tiles W_jj (identity solved against L_jj) and
+// alpha = L^-T z by backward substitution over tiles, alpha_j = W_jj' (z_j - sum_{i>j} L_ij' alpha_i).
+// Replaces posterior(fx, y) [upstream AbstractGPs] for every row of an MCMC chain at once (gaplac_b200/chain.py).
+size_t lk_post_smem_bytes() { return (size_t)(TILE_ELEMS + DSIZE + 2 * TS) * sizeof(double); }
+
+__global__ void __launch_bounds__(NTHREADS) lk_post_kernel(const __grid_constant__ LkPostParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *S = reinterpret_cast<double *>(smem_raw), *D = S + TILE_ELEMS, *rbuf = D + DSIZE, *abuf = rbuf + TS;
+    const int tid = threadIdx.x, b = blockIdx.x, nt = prm.nt;
+    const TMap tm = thread_map(tid);
+    const long long ntri = tri_index(nt, 0);
+    const double *L = prm.tiles + (size_t)b * ntri * TILE_ELEMS;
+    const double *Dg = prm.dblk + (size_t)b * nt * DSIZE;
+    const double *z = prm.z + (size_t)b * nt * TS;
+    double *W = prm.winv + (size_t)b * nt * TILE_ELEMS;
+    double *alpha = prm.alpha + (size_t)b * nt * TS;
+    for (int j = 0; j < nt; ++j) {
+        __syncthreads();
+        tile_load_async(S, L + tri_index(j, j) * TILE_ELEMS, tid);
+        block_load_async<DSIZE * 8>(D, Dg + (size_t)j * DSIZE, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double e[2][NCC];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int cc = 0; cc < NCC; ++cc) e[mb][cc] = (row_of(tm, mb) == col_of(tm, cc)) ? 1.0 : 0.0;
+        tile_trsm_ld(e, S, D, tm);
+        acc_to_tile_t(W + (size_t)j * TILE_ELEMS, e, tm);
+    }
+    for (int j = nt - 1; j >= 0; --j) {
+        double rj = 0.0;
+        if (tid < TS) rj = z[j * TS + tid];
+        for (int i = nt - 1; i > j; --i) {
+            __syncthreads();
+            tile_load_async(S, L + tri_index(i, j) * TILE_ELEMS, tid);
+            cp_async_commit();
+            if (tid < TS) abuf[tid] = alpha[i * TS + tid];  // written by this thread in an earlier step
+            cp_async_wait<0>();
+            __syncthreads();
+            if (tid < TS) rj -= tile_col_dot(S, abuf, tid);
+        }
+        __syncthreads();  // also orders the W stores above before this CTA's loads of them
+        tile_load_async(S, W + (size_t)j * TILE_ELEMS, tid);
+        cp_async_commit();
+        if (tid < TS) rbuf[tid] = rj;
+        cp_async_wait<0>();
+        __syncthreads();
+        if (tid < TS) alpha[j * TS + tid] = tile_col_dot(S, rbuf, tid);  // W upper part is zero
+    }
+}
+
 }  // namespace gpl

@@ -36,13 +36,24 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
     const int n = prm.n, nt = prm.nt, m = prm.m;
     double *const part = sm.A;  // 32 * TS doubles, used between the tile loops only
     double *wsV = prm.wsV + (size_t)blockIdx.x * nt * TILE_ELEMS;
-    prepare_item_scalars(P, prm.theta, &sm.sc, tid);
-    __syncthreads();
+    const int items = prm.items > 0 ? prm.items : 1;
+    int cur = -1;
 
     constexpr int WS = 8 * NB, MASK = (1 << NB) - 1;  // slab width, active n-blocks
     static_assert(NB % 2 == 0 && NB >= 2 && NB <= 8, "whole 16-column quarters");
     const int nslab = (m + WS - 1) / WS;
-    for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
+    for (long long u = blockIdx.x; u < (long long)items * nslab; u += gridDim.x) {
+        const int b = (int)(u / nslab), s = (int)(u - (long long)b * nslab);
+        if (b != cur) {  // a new posterior: its hyperparameters
+            __syncthreads();
+            prepare_item_scalars(P, prm.theta + b * prm.theta_stride, &sm.sc, tid);
+            __syncthreads();
+            cur = b;
+        }
+        const double *tiles = prm.tiles + b * prm.tiles_stride, *winv = prm.winv + b * prm.winv_stride;
+        const double *alpha = prm.alpha + b * prm.alpha_stride;
+        double *mean = prm.mean + (size_t)b * m, *var = prm.var ? prm.var + (size_t)b * m : nullptr;
+        const bool bad = prm.info && prm.info[b] != 0;  // not positive definite: NaN, like the lml's -Inf
         int gj[NCC];
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) gj[cc] = s * WS + col_of(tm, cc);
@@ -57,7 +68,7 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
             eval_block_acc<false>(P, sm.sc, prm.X, n, n, gi, prm.Xs, m, m, s * WS, tm.t, 0.0, acc, NB / 2);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-                const double al = gi[mb] < n ? prm.alpha[gi[mb]] : 0.0;
+                const double al = gi[mb] < n ? alpha[gi[mb]] : 0.0;
 #pragma unroll
                 for (int cc = 0; cc < NCC; ++cc) cmean[cc] = fma(acc[mb][cc], al, cmean[cc]);
             }
@@ -65,7 +76,7 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
             // acc -= sum_{k<i} L_ik V_k : row operand L_ik, column operand V_k' (stored transposed)
             for (int k = 0; k < i; ++k) {
                 __syncthreads();
-                tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+                tile_load_async(sm.A, tiles + tri_index(i, k) * TILE_ELEMS, tid);
                 tile_load_async(sm.Bt, wsV + (size_t)k * TILE_ELEMS, tid);
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -74,7 +85,7 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
             }
             // V_i = W_ii acc  (W lower triangular: rows of this warp need k < r0 + 16)
             __syncthreads();
-            tile_load_async(sm.A, prm.winv + (size_t)i * TILE_ELEMS, tid);
+            tile_load_async(sm.A, winv + (size_t)i * TILE_ELEMS, tid);
             cp_async_commit();
             acc_to_tile_t(sm.Bt, acc, tm);
             cp_async_wait<0>();
@@ -97,7 +108,7 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
             double sum = 0.0;
 #pragma unroll 8
             for (int gq = 0; gq < 32; ++gq) sum += part[gq * TS + tid];
-            prm.mean[s * WS + tid] = sum;
+            mean[s * WS + tid] = bad ? NAN : sum;
         }
         if (prm.want_var) {
             __syncthreads();
@@ -112,7 +123,7 @@ __device__ __forceinline__ void predict_body(const PredictParams &prm) {
                 int one_i[1] = {s * WS + tid}, one_j[1] = {s * WS + tid};
                 double kss[1][1];
                 eval_block<1, 1, false>(P, sm.sc, prm.Xs, m, m, one_i, prm.Xs, m, m, one_j, 0.0, kss);
-                prm.var[s * WS + tid] = kss[0][0] - sum;
+                var[s * WS + tid] = bad ? NAN : kss[0][0] - sum;
             }
         }
         __syncthreads();

@@ -137,6 +137,18 @@ int gpl_posterior_factor(gpl_post *post, double *U);    /* n x n upper factor (K
  * Xs is m x d column-major. var may be NULL. Tiled over m: K* is never materialised. */
 int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean, double *var);
 
+/* ---- batched posteriors + predictions: the loop behind the `predict` / `fitplot` commands ----------------
+ * For every row b of a chain of hyperparameter draws (Theta p x B; sigma2 shared or per row):
+ *   post_b = posterior(FiniteGP(GP(kernel(theta_b)), X, sigma2_b), y);  mean_and_var(post_b, Xs)
+ * (src/plotting.jl:6-12 per row; commands stubbed at CLI/src/main.jl:8-16, output columns test/pred.jl:11-14).
+ * X (n x d) and y (n) are shared by the rows.  mean, var: m x B column-major (row b at b*m; var may be NULL);
+ * lml (B, optional) and info (B, optional) as in gpl_lml_batched: a row whose covariance is not positive
+ * definite has info[b] != 0, lml[b] = -Inf and NaN predictions.  All rows are factored in one batch; returns
+ * GPL_ERR_LIMIT when B rows of size n exceed the factor workspace cap ("lk_ws_limit_mb"): split the chain. */
+int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
+                        const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter, int B,
+                        int m, const double *Xs, double *mean, double *var, double *lml, int *info);
+
 /* ---- prior sample: replaces rand(gp(X, sigma2)) (CLI/src/sample.jl:25) --------------------------------
  * out (n x S) = U' Z with caller-supplied standard normals Z (n x S): the RNG stays in the host. */
 int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,

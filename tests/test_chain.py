@@ -61,6 +61,8 @@ def test_predict_chain_golden_model_matches_oracle():
     Xs = np.column_stack([np.zeros_like(nut), np.zeros_like(nut), nut])
     gp = G.GP(KernelProgram(ops=ops, vars=["PersonID", "StoolPairs", "nutrient"], n_theta=4))
     out = G.predict_chain(gp, X, y, Th[rows], Xs, sigma2=0.0, jitter=1e-9, obs_var=Th[rows, 3])
+    loop = G.predict_chain(gp, X, y, Th[rows], Xs, sigma2=0.0, jitter=1e-9, obs_var=Th[rows, 3], batched=False)
+    assert np.max(np.abs(out["mu"] - loop["mu"])) < 1e-9 and np.max(np.abs(out["var"] - loop["var"])) < 1e-9
     mu = np.empty((len(rows), len(nut)))
     var = np.empty_like(mu)
     for k, r in enumerate(rows):
@@ -73,3 +75,42 @@ def test_predict_chain_golden_model_matches_oracle():
     assert np.allclose(out["fmu"], fm, atol=1e-8) and np.allclose(out["ymu"], ym, atol=1e-8)
     assert np.allclose(out["yQ050"], yQ[0], atol=1e-7) and np.allclose(out["yQ950"], yQ[2], atol=1e-7)
     assert np.all(out["yQ950"] - out["yQ050"] > out["fQ950"] - out["fQ050"])   # observation noise widens the band
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,B", [(50, 7, 3), (130, 200, 5), (300, 33, 2)])
+def test_predict_batched_matches_oracle_per_row(n, m, B):
+    """gpl_predict_batched (lockstep factorisation of all rows + lk_post_kernel + batched prediction kernel) against the
+    oracle's posterior / mean_and_var row by row: ragged n, per-row sigma2, a non-PD row reported through info."""
+    from gaplac_b200._lib import ADD, CAT, CONSTANT, LINEAR, MUL, NOISE, OU, SQEXP
+    from gaplac_b200.formula import Op
+    ALL_KINDS = [Op(SQEXP, col=0, theta_slot=0, var_slot=3), Op(OU, col=1, theta_slot=1), Op(MUL),
+                 Op(LINEAR, col=2, theta_slot=2), Op(CAT, col=3), Op(MUL, var=0.7), Op(ADD),
+                 Op(CONSTANT, value=0.3), Op(ADD), Op(NOISE, var_slot=4), Op(ADD)]
+    THETA = np.array([1.3, 0.8, 0.4, 1.7, 0.2])
+
+    def _data(k, seed=0):
+        rng = np.random.default_rng(seed)
+        return (np.column_stack([rng.uniform(-3, 3, k), rng.uniform(0, 5, k), rng.standard_normal(k),
+                                 rng.integers(0, 4, k).astype(float)]), rng.standard_normal(k))
+    ctx = G.default_context()
+    X, y = _data(n, seed=40 + n)
+    Xs, _ = _data(m, seed=41 + n)
+    prog = ctx.program(ALL_KINDS)
+    Th = np.vstack([THETA * (1.0 + 0.07 * b) for b in range(B)])
+    s2 = np.linspace(0.08, 0.2, B)
+    mean, var, lml, info = ctx.predict_batched(prog, X, y, Th, s2, Xs)
+    assert not info.any()
+    for b in range(B):
+        U, alpha = CO.posterior(ALL_KINDS, X, y, Th[b], float(s2[b]))
+        rm, rv = CO.mean_and_var(ALL_KINDS, X, U, alpha, Xs, Th[b])
+        ref, _ = CO.lml(ALL_KINDS, X, y, Th[b], float(s2[b]))
+        assert abs(lml[b] - ref) < 1e-9 * abs(ref)
+        assert np.max(np.abs(mean[b] - rm)) < 1e-8 * max(1.0, np.max(np.abs(rm)))
+        assert np.max(np.abs(var[b] - rv)) < 1e-8 * max(1.0, np.max(np.abs(rv)))
+    Thb = Th.copy()
+    Thb[1, 3] = -50.0                       # negative variance on the SqExp*OU term: row 1 is not positive definite
+    mean, var, lml, info = ctx.predict_batched(prog, X, y, Thb, s2, Xs)
+    if B > 1:
+        assert info[1] != 0 and np.isinf(lml[1]) and np.all(np.isnan(mean[1])) and np.all(np.isnan(var[1]))
+        assert info[0] == 0 and np.all(np.isfinite(mean[0]))
