@@ -141,6 +141,23 @@ function AbstractGPs.mean_and_var(p::B200Posterior, xtest)
         (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), p.h, m, Xs, mu, v))
     return mu, v
 end
+# The loop behind `predict` / `fitplot` (CLI/src/main.jl:8-16): one posterior per column of Theta (p x B chain of
+# hyperparameter draws) over the same (X, y), mean and variance at xtest for each - one library call.
+# Returns (mean m x B, var m x B, lml B, info B); rows with info != 0 were not positive definite (NaN predictions).
+function predict_chain(fx::B200FiniteGP, y::AbstractVector{<:Real}, Theta::Matrix{Float64}, xtest;
+                       sigma2 = [noisevar(fx)], jitter::Float64 = 0.0)
+    X = rowmatrix(fx.x); n, d = size(X); p, B = size(Theta); Xs = rowmatrix(xtest); m = size(Xs, 1)
+    yv = Vector{Float64}(y); s2 = Vector{Float64}(sigma2)
+    mu = Matrix{Float64}(undef, m, B); v = Matrix{Float64}(undef, m, B)
+    lml = Vector{Float64}(undef, B); info = zeros(Cint, B)
+    GC.@preserve X yv Theta s2 Xs mu v lml info check(ctx().h, ccall((:gpl_predict_batched, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64,
+         Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx().h, fx.f.kernel.prog.h, n, d, X, yv, Theta, p, s2, length(s2) == B && B > 1 ? 1 : 0, jitter, B, m, Xs,
+        mu, v, lml, info))
+    return mu, v, lml, info
+end
+
 function Base.rand(rng::Random.AbstractRNG, fx::B200FiniteGP; theta = Float64[], jitter = 0.0)
     X = rowmatrix(fx.x); n, d = size(X); z = randn(rng, n); out = similar(z)   # the RNG stays Julia's
     GC.@preserve X z out theta check(ctx().h, ccall((:gpl_sample, LIB), Cint,
