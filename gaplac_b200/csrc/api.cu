@@ -39,7 +39,8 @@ struct gpl_ctx {
     char name[128] = {0};
     cudaStream_t stream = nullptr;
     cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
-    DevBuf bigFlags, bigD, lkW, lkAlpha;
+    DevBuf bigFlags, bigD, lkW, lkAlpha, dStage;
+    void *hStage = nullptr;  // pinned host staging block of the small-call path (gpl_lml_batched)
     std::vector<std::pair<void *, size_t>> postFree;  // device blocks of freed posteriors (cudaMalloc / cudaFree cost
                                                       // milliseconds next to multi-GB workspaces: a refit reuses them)
     uint64_t launches = 0;
@@ -528,12 +529,13 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &blk : ctx->postFree) cudaFree(blk.first);
+    if (ctx->hStage) cudaFreeHost(ctx->hStage);
     if (ctx->s_worker) cudaStreamDestroy(ctx->s_worker);
     if (ctx->s_panel) cudaStreamDestroy(ctx->s_panel);
     if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
@@ -672,6 +674,39 @@ int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const doub
         (rc = ensure(ctx, ctx->bInfo, (size_t)B * 4)))
         return rc;
     const bool grad = dtheta != nullptr || dy != nullptr;
+    {
+        // Small calls (one log-density + gradient evaluation of an MCMC step: a few KB) are bound by driver calls, not by
+        // bytes: pack every input into one pinned block -> one H2D copy, and every output into one D2H copy.
+        constexpr size_t STAGE = 1 << 20;
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t o_x = 0, o_y = o_x + up(xb), o_t = o_y + up(yb), o_s = o_t + up((size_t)p * B * 8), in_bytes = o_s + up(sb);
+        const size_t r_lml = up(in_bytes), r_info = r_lml + up((size_t)B * 8), r_dth = r_info + up((size_t)B * 4),
+                     r_dy = r_dth + (grad ? up((size_t)(p > 0 ? p : 1) * B * 8) : 0), end = r_dy + (grad ? up((size_t)n * B * 8) : 0);
+        if (end <= STAGE) {
+            if (!ctx->hStage) CU(ctx, cudaHostAlloc(&ctx->hStage, STAGE, cudaHostAllocDefault));
+            if ((rc = ensure(ctx, ctx->dStage, STAGE))) return rc;
+            char *h = static_cast<char *>(ctx->hStage), *dv = static_cast<char *>(ctx->dStage.p);
+            memcpy(h + o_x, X, xb);
+            memcpy(h + o_y, Y, yb);
+            if (p > 0) memcpy(h + o_t, Theta, (size_t)p * B * 8);
+            memcpy(h + o_s, sigma2, sb);
+            CU(ctx, cudaMemcpyAsync(dv, h, in_bytes, cudaMemcpyHostToDevice, st));
+            rc = launch_lml(ctx, prog->dev, n, d, reinterpret_cast<double *>(dv + o_x), x_batched,
+                            reinterpret_cast<double *>(dv + o_y), y_batched, reinterpret_cast<double *>(dv + o_t), p,
+                            reinterpret_cast<double *>(dv + o_s), sigma2_batched, jitter, B,
+                            reinterpret_cast<double *>(dv + r_lml), grad ? reinterpret_cast<double *>(dv + r_dth) : nullptr,
+                            grad ? reinterpret_cast<double *>(dv + r_dy) : nullptr, reinterpret_cast<int *>(dv + r_info),
+                            grad ? 1 : 0, 0, nullptr, nullptr, st);
+            if (rc) return rc;
+            CU(ctx, cudaMemcpyAsync(h + r_lml, dv + r_lml, end - r_lml, cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+            memcpy(lml, h + r_lml, (size_t)B * 8);
+            if (info) memcpy(info, h + r_info, (size_t)B * 4);
+            if (dtheta && p > 0) memcpy(dtheta, h + r_dth, (size_t)p * B * 8);
+            if (dy) memcpy(dy, h + r_dy, (size_t)n * B * 8);
+            return GPL_OK;
+        }
+    }
     if (grad && ((rc = ensure(ctx, ctx->bDtheta, tb)) || (rc = ensure(ctx, ctx->bDy, (size_t)n * B * 8)))) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, xb, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->bY.p, Y, yb, cudaMemcpyHostToDevice, st));
