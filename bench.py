@@ -373,7 +373,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                         "algorithmic_flops": flops}},
             "e2e": {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e_ms,
-                    "api": "gpl_lml_batched (host buffers, blocking) via ctypes"},
+                    "api": "gpl_lml_batched (caller-owned host buffers, blocking; the library packs them into one pinned block: one H2D + one D2H copy per step) via ctypes"},
             "gpu_launches": int(launches), "clocks": clocks, "not_pd_items": bad, "arms_max_rel_diff": parity,
         }
         if world == 1 and not args.no_cpu:
