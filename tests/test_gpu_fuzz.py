@@ -79,3 +79,35 @@ def test_random_program_against_oracle(ctx, case):
     assert abs(lml2[0] - ref) <= 1e-9 * abs(ref) and lml2[0] == lml2[1]
     assert np.max(np.abs(dth[0] - rdth) / np.maximum(1.0, np.abs(rdth))) < 1e-8
     assert np.max(np.abs(dy[0] - rdy)) < 1e-8 * max(1.0, np.max(np.abs(rdy)))
+
+
+@pytest.mark.parametrize("case", range(0, 40, 3))
+def test_random_program_posterior_and_predictions(ctx, case):
+    """Same random formulas through posterior_fit / mean_and_var and the batched chain path."""
+    rng = np.random.default_rng(1000 + case)
+    ops = _random_program(rng)
+    n = int(rng.choice([5, 64, 100, 150]))
+    m = int(rng.choice([1, 40, 100]))
+    X = np.column_stack([rng.uniform(-3, 3, n), rng.uniform(0, 5, n), rng.standard_normal(n),
+                         rng.integers(0, 4, n).astype(float)])
+    Xs = np.column_stack([rng.uniform(-3, 3, m), rng.uniform(0, 5, m), rng.standard_normal(m),
+                          rng.integers(0, 4, m).astype(float)])
+    y = rng.standard_normal(n)
+    Th = rng.uniform(0.4, 1.6, (3, P_SLOTS))
+    sigma2 = float(rng.uniform(0.3, 1.0))
+    try:
+        prog = ctx.program(ops)
+    except _lib.GaplacError:
+        return
+    post = ctx.posterior_fit(prog, X, y, Th[0], sigma2, 1e-10)
+    mean, var = post.mean_and_var(Xs)
+    post.free()
+    bm, bv, blml, binfo = ctx.predict_batched(prog, X, y, Th, sigma2, Xs, 1e-10)
+    assert not binfo.any()
+    for b in range(3):
+        U, alpha = O.posterior(ops, X, y, Th[b], sigma2, 1e-10)
+        rm, rv = O.mean_and_var(ops, X, U, alpha, Xs, Th[b])
+        tol_m, tol_v = 1e-8 * max(1.0, np.max(np.abs(rm))), 1e-8 * max(1.0, np.max(np.abs(rv)))
+        assert np.max(np.abs(bm[b] - rm)) < tol_m and np.max(np.abs(bv[b] - rv)) < tol_v
+        if b == 0:
+            assert np.max(np.abs(mean - rm)) < tol_m and np.max(np.abs(var - rv)) < tol_v
