@@ -24,7 +24,7 @@ SYMBOLS = [
     "gpl_cov", "gpl_cov_dev", "gpl_cross_cov", "gpl_lml_batched", "gpl_lml_batched_dev", "gpl_posterior_fit",
     "gpl_posterior_free", "gpl_posterior_logpdf", "gpl_posterior_alpha", "gpl_posterior_factor",
     "gpl_posterior_mean_var", "gpl_sample", "gpl_chol_logdet", "gpl_chol_logdet_dev", "gpl_lml_large",
-    "gpl_predict_batched",
+    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream",
 ]
 
 
@@ -32,6 +32,11 @@ class GplOp(C.Structure):
     """struct gpl_op (32 bytes)."""
     _fields_ = [("kind", C.c_int32), ("col", C.c_int32), ("theta_slot", C.c_int32), ("var_slot", C.c_int32),
                 ("value", C.c_double), ("var", C.c_double)]
+
+
+class GplTiming(C.Structure):
+    """struct gpl_timing."""
+    _fields_ = [("n_phases", C.c_int32), ("launches", C.c_int32 * 8), ("ms", C.c_double * 8)]
 
 
 class GaplacError(RuntimeError):
@@ -74,6 +79,8 @@ def load() -> C.CDLL:
     lib.gpl_destroy.argtypes = [_vp]
     lib.gpl_set_option.argtypes = [_vp, C.c_char_p, C.c_int]
     lib.gpl_device_info.argtypes = [_vp, C.c_char_p, C.c_int, _ip, _ip]
+    lib.gpl_last_timing.argtypes = [_vp, C.POINTER(GplTiming)]
+    lib.gpl_set_stream.argtypes = [_vp, _vp]
     lib.gpl_program_create.argtypes = [_vp, C.POINTER(GplOp), C.c_int, C.POINTER(_vp)]
     lib.gpl_program_destroy.argtypes = [_vp]
     lib.gpl_program_n_theta.argtypes = [_vp]
@@ -235,6 +242,16 @@ class Context:
         sm, clk = C.c_int(), C.c_int()
         _check(self.h, load().gpl_device_info(self.h, name, 128, C.byref(sm), C.byref(clk)))
         return name.value.decode(), sm.value, clk.value
+
+    def set_stream(self, stream: int = 0) -> None:
+        """Host entry points run on this CUDA stream (raw cudaStream_t, e.g. torch.cuda.Stream.cuda_stream); 0 restores."""
+        _check(self.h, load().gpl_set_stream(self.h, stream or None))
+
+    def last_timing(self):
+        """(ms[7], launches[7]) per phase of the last call made with option profile_events = 1 (gpl_last_timing)."""
+        t = GplTiming()
+        _check(self.h, load().gpl_last_timing(self.h, C.byref(t)))
+        return np.array(t.ms[: t.n_phases]), np.array(t.launches[: t.n_phases])
 
     def program(self, ops) -> Program:
         return Program(self, ops)

@@ -111,14 +111,36 @@ def predict_chain(gp: "_gp.GP", X, y, chain_theta, Xtest, sigma2=0.0, jitter: fl
     return out
 
 
+def log2_harmmean_exp2(lp_chain) -> float:
+    """log2(harmmean(2 .^ lp)) exactly as `select --chains` computes it (CLI/src/select.jl:15-19, there with BigFloat
+    powers of two), as a stable base-2 log-sum-exp:  log2 S - log2 sum_i 2^(-lp_i).  The reference treats the chain's
+    natural-log densities as base-2 exponents; this reproduces that number, quirk included."""
+    lp = np.asarray(lp_chain, dtype=np.float64)
+    m = np.max(-lp)
+    return float(np.log2(lp.size) - (m + np.log2(np.sum(np.exp2(-lp - m)))))
+
+
+def select_chains_log2_bayes(lp_chain_1, lp_chain_2) -> float:
+    """The "Log2 Bayes" figure of `select --chains a.tsv b.tsv` (CLI/src/select.jl:15-20): lp1 - lp2 with
+    lp_k = log2(harmmean(2 .^ lp_k_chain)).  Positive values favour model 1 (select.jl:65)."""
+    return log2_harmmean_exp2(lp_chain_1) - log2_harmmean_exp2(lp_chain_2)
+
+
+def select_formulae_log2_bayes(lp1: float, lp2: float) -> float:
+    """`select --formulae`: log2(2^lp1 / 2^lp2) = lp1 - lp2 (CLI/src/select.jl:54)."""
+    return float(lp1) - float(lp2)
+
+
 def log_evidence_harmonic(loglik_chain) -> float:
-    """log of the harmonic-mean evidence estimate of a chain of log-likelihoods, as a stable log-sum-exp:
-    log Z = log S - logsumexp(-ll).  (The reference reaches for BigFloat powers instead: CLI/src/select.jl:15-20.)"""
+    """NOT the reference's number: the natural-log harmonic-mean evidence estimate  log Z = log S - logsumexp(-ll)  of a
+    chain of log-likelihoods - what the reference's base-2 expression (see log2_harmmean_exp2) would be if it exponentiated
+    with e.  Offered as the statistically meaningful variant; `select_chains_log2_bayes` is the drop-in."""
     ll = np.asarray(loglik_chain, dtype=np.float64)
     m = np.max(-ll)
     return float(np.log(ll.size) - (m + np.log(np.sum(np.exp(-ll - m)))))
 
 
 def log_bayes_factor(loglik_chain_1, loglik_chain_2) -> float:
-    """log10 Bayes factor of model 1 over model 2 from two chains (`select --chains`)."""
+    """log10 Bayes factor of model 1 over model 2 from the natural-log harmonic means (a deliberate departure from the
+    reference's base-2 figure; see select_chains_log2_bayes for that one)."""
     return (log_evidence_harmonic(loglik_chain_1) - log_evidence_harmonic(loglik_chain_2)) / np.log(10.0)

@@ -37,10 +37,14 @@ struct gpl_ctx {
     int sm_count = 0;
     int clock_khz = 0;
     char name[128] = {0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream host entry points run on (own_stream, or the caller's: gpl_set_stream)
+    cudaStream_t own_stream = nullptr;
     cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
     DevBuf bigFlags, bigD, lkW, lkAlpha, dStage;
     void *hStage = nullptr;  // pinned host staging block of the small-call path (gpl_lml_batched)
+    std::vector<gpl_post *> livePosts;  // posteriors created on this context and not yet freed (gpl_destroy detaches them)
+    cudaEvent_t wsEvent = nullptr;      // completion of the last call that used the shared workspace (any stream)
+    bool wsEventSet = false;
     std::vector<std::pair<void *, size_t>> postFree;  // device blocks of freed posteriors (cudaMalloc / cudaFree cost
                                                       // milliseconds next to multi-GB workspaces: a refit reuses them)
     uint64_t launches = 0;
@@ -49,12 +53,12 @@ struct gpl_ctx {
     int lml_variant = 0;
     int chol_variant = 0;
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
-    size_t lk_ws_limit = (size_t)12 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
+    size_t lk_ws_limit = (size_t)24 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
-    double lk_ms[3] = {0, 0, 0};            // last instrumented call: total ms in diag / potrf / below kernels
-    int lk_launches[3] = {0, 0, 0};
+    double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
+    int lk_launches[7] = {0, 0, 0, 0, 0, 0, 0};  // alpha / contraction kernels
     // grow-only device buffers
-    DevBuf lkTiles, lkD, lkZ, lkAcc;
+    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
 };
 
@@ -94,9 +98,23 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
                         __LINE__);                                                                            \
     } while (0)
 
+// The context owns ONE grow-only workspace.  Calls may arrive on different streams (the *_dev entry points take the
+// caller's stream): every call that touches the workspace first makes its stream wait for the previous such call and
+// records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
+struct WsOrder {
+    gpl_ctx *c;
+    cudaStream_t st;
+    WsOrder(gpl_ctx *ctx, cudaStream_t s) : c(ctx), st(s) {
+        if (c->wsEventSet) cudaStreamWaitEvent(st, c->wsEvent, 0);
+    }
+    ~WsOrder() {
+        if (c->wsEvent && cudaEventRecord(c->wsEvent, st) == cudaSuccess) c->wsEventSet = true;
+    }
+};
+
 int ensure(gpl_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return GPL_OK;
-    if (b.p) CU(ctx, cudaFree(b.p));
+    if (b.p) CU(ctx, cudaFree(b.p));  // (cudaFree synchronises the device: nothing in flight can still read the old block)
     b.p = nullptr;
     b.cap = 0;
     size_t want = bytes + bytes / 8 + 256;
@@ -122,14 +140,15 @@ int check_prog_args(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, int p) {
 // ---- launch helpers ------------------------------------------------------------------------------------------
 int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
                         const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
-                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st);
+                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st,
+                        double *ddtheta = nullptr, double *ddy = nullptr, int want_grad = 0);
 int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched, const double *dY,
                int y_batched, const double *dTheta, int p, const double *dsigma2, int sigma2_batched, double jitter,
                int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
                double *keep_ws, double *keep_vec, cudaStream_t st) {
-    if (!want_grad && !keep && ctx->lml_variant != 1)
+    if (!keep && ctx->lml_variant != 1)
         return launch_lml_lockstep(ctx, prog, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
-                                   dlml, dinfo, st);
+                                   dlml, dinfo, st, ddtheta, ddy, want_grad);
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     const long long tiles_per_cta = ntri + nt + (want_grad ? ntri : 0);
@@ -193,10 +212,12 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
     return GPL_OK;
 }
 
-// lockstep schedule for plain log-likelihoods (no gradient, nothing kept): 3 kernels per tile column over the batch
+// lockstep schedule: 2 kernels per tile column over the batch; with want_grad the gradient phases of
+// lml_grad_lockstep.cu follow (W_jj, M = L^-1 row by row, alpha, K^-1 tiles contracted with dK/dtheta)
 int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
                         const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
-                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st) {
+                        int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st,
+                        double *ddtheta, double *ddy, int want_grad) {
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     if (!ctx->attr_lk) {
@@ -205,15 +226,23 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
         CU(ctx, cudaFuncSetAttribute(lk_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_potrf_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_potrf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)lk_potrf_warp_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_winv_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+        CU(ctx, cudaFuncSetAttribute(lk_gradc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_grad_smem_bytes()));
         ctx->attr_lk = true;
     }
-    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16;
+    const size_t grad_item = want_grad ? (size_t)(ntri + nt) * TILE_BYTES + (size_t)nt * TS * 8 + (size_t)ntri * (p > 0 ? p : 1) * 8 : 0;
+    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16 + grad_item;
     int Bc = (int)(ctx->lk_ws_limit / per_item);
     if (Bc < 1) Bc = 1;
     if (Bc > B) Bc = B;
     int rc;
     if ((rc = ensure(ctx, ctx->lkTiles, (size_t)Bc * ntri * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkD, (size_t)Bc * nt * DSIZE * 8)) ||
         (rc = ensure(ctx, ctx->lkZ, (size_t)Bc * nt * TS * 8)) || (rc = ensure(ctx, ctx->lkAcc, (size_t)Bc * 16)))
+        return rc;
+    if (want_grad && ((rc = ensure(ctx, ctx->lkM, (size_t)Bc * ntri * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkW, (size_t)Bc * nt * TILE_BYTES)) ||
+                      (rc = ensure(ctx, ctx->lkAlpha, (size_t)Bc * nt * TS * 8)) ||
+                      (rc = ensure(ctx, ctx->lkGpart, (size_t)Bc * ntri * (p > 0 ? p : 1) * 8))))
         return rc;
     int *info_dev = dinfo;
     if (!info_dev) {
@@ -243,7 +272,22 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     pp.acc2 = ptr<double>(ctx->lkAcc);
     std::vector<cudaEvent_t> evs;
     std::vector<int> ev_kind;
-    auto mark = [&](int kind) {  // kind: 0 diag, 1 potrf, 2 below, -1 start
+    LkGradParams gp;
+    gp.prog = prog;
+    gp.n = n;
+    gp.d = d;
+    gp.nt = nt;
+    gp.p = p;
+    gp.i = 0;
+    gp.x_stride = prm.x_stride;
+    gp.tiles = prm.tiles;
+    gp.dblk = prm.dblk;
+    gp.z = prm.z;
+    gp.winv = ptr<double>(ctx->lkW);
+    gp.minv = ptr<double>(ctx->lkM);
+    gp.alpha = ptr<double>(ctx->lkAlpha);
+    gp.gpart = ptr<double>(ctx->lkGpart);
+    auto mark = [&](int kind) {  // kind: 0 diag, 1 potrf, 2 below, 3..6 gradient phases (winv, minv, alpha, contraction), -1 start
         if (!ctx->profile_events) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -286,11 +330,37 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
                 ctx->launches++;
             }
         }
+        if (want_grad) {
+            gp.X = prm.X;
+            gp.Theta = prm.Theta;
+            gp.info = pp.info;
+            gp.B = nb;
+            gp.dtheta = ddtheta ? ddtheta + (size_t)off * p : nullptr;
+            gp.dy = ddy ? ddy + (size_t)off * n : nullptr;
+            lk_winv_kernel<<<(unsigned)((size_t)nb * nt), NTHREADS, lk_winv_smem_bytes(), st>>>(gp);
+            ctx->launches++;
+            mark(3);
+            for (int i = 1; i < nt; ++i) {
+                gp.i = i;
+                lk_minv_kernel<<<(unsigned)((size_t)nb * i), NTHREADS, TILE_BYTES, st>>>(gp);
+                ctx->launches++;
+                mark(4);
+            }
+            lk_alpha_kernel<<<(unsigned)((size_t)nb * nt), NTHREADS, 0, st>>>(gp);
+            ctx->launches++;
+            mark(5);
+            if (p > 0 && ddtheta) {
+                lk_gradc_kernel<<<(unsigned)((size_t)nb * ntri), NTHREADS, lk_grad_smem_bytes(), st>>>(gp);
+                lk_gradsum_kernel<<<(nb + 127) / 128, 128, 0, st>>>(gp);
+                ctx->launches += 2;
+                mark(6);
+            }
+        }
     }
     CU(ctx, cudaGetLastError());
     if (ctx->profile_events) {
         CU(ctx, cudaStreamSynchronize(st));
-        for (int k = 0; k < 3; ++k) ctx->lk_ms[k] = 0.0, ctx->lk_launches[k] = 0;
+        for (int k = 0; k < 7; ++k) ctx->lk_ms[k] = 0.0, ctx->lk_launches[k] = 0;
         for (size_t e = 1; e < evs.size(); ++e) {
             if (ev_kind[e] >= 0) {
                 float ms = 0.f;
@@ -508,7 +578,9 @@ int gpl_init(int device, gpl_ctx **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->wsEvent, cudaEventDisableTiming)) != cudaSuccess) {
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return fail(nullptr, GPL_ERR_CUDA, "gpl_init: %s", cudaGetErrorString(e));
     }
@@ -518,6 +590,7 @@ int gpl_init(int device, gpl_ctx **out) {
         return fail(nullptr, GPL_ERR_CUDA, "gpl_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     }
+    ctx->own_stream = ctx->stream;
     ctx->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device);
     snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
@@ -528,8 +601,18 @@ int gpl_init(int device, gpl_ctx **out) {
 int gpl_destroy(gpl_ctx *ctx) {
     if (!ctx) return GPL_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
+    cudaDeviceSynchronize();  // *_dev calls may still be in flight on caller streams
+    // Posteriors that outlive their context are detached: their device block is released here, the host handle stays
+    // valid for gpl_posterior_free (which then only deletes it); every other call on such a handle returns GPL_ERR_ARG.
+    for (gpl_post *post : ctx->livePosts) {
+        if (post->block) cudaFree(post->block);
+        post->block = nullptr;
+        post->tiles = post->winv = post->alpha = post->dX = post->dtheta = nullptr;
+        post->ctx = nullptr;
+    }
+    ctx->livePosts.clear();
+    if (ctx->wsEvent) cudaEventDestroy(ctx->wsEvent);
+    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->lkM, &ctx->lkGpart, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
                       &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
                       &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
     for (DevBuf *b : bufs)
@@ -539,8 +622,17 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (ctx->s_worker) cudaStreamDestroy(ctx->s_worker);
     if (ctx->s_panel) cudaStreamDestroy(ctx->s_panel);
     if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return GPL_OK;
+}
+
+int gpl_set_stream(gpl_ctx *ctx, void *stream) {
+    if (!ctx) return fail(ctx, GPL_ERR_ARG, "gpl_set_stream: null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
     return GPL_OK;
 }
 
@@ -605,6 +697,7 @@ int gpl_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, c
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bTheta, (size_t)(p + 1) * 8)) ||
         (rc = ensure(ctx, ctx->bK, (size_t)n * n * 8)))
         return rc;
@@ -626,6 +719,7 @@ int gpl_cross_cov(gpl_ctx *ctx, const gpl_prog *prog, int n, int m, int d, const
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bXs, (size_t)m * d * 8)) ||
         (rc = ensure(ctx, ctx->bTheta, (size_t)(p + 1) * 8)) || (rc = ensure(ctx, ctx->bK, (size_t)n * m * 8)))
         return rc;
@@ -651,6 +745,7 @@ int gpl_lml_batched_dev(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
     if (!dX || !dY || !dsigma2 || !dlml || (p > 0 && !dTheta)) return fail(ctx, GPL_ERR_ARG, "gpl_lml_batched: null pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, (cudaStream_t)stream);
     const int want_grad = ddtheta != nullptr;
     return launch_lml(ctx, prog->dev, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
                       dlml, ddtheta, ddy, dinfo, want_grad, 0, nullptr, nullptr, (cudaStream_t)stream);
@@ -667,6 +762,7 @@ int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const doub
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     const size_t xb = (size_t)n * d * (x_batched ? B : 1) * 8, yb = (size_t)n * (y_batched ? B : 1) * 8;
     const size_t tb = (size_t)(p > 0 ? p : 1) * B * 8, sb = (size_t)(sigma2_batched ? B : 1) * 8;
     if ((rc = ensure(ctx, ctx->bX, xb)) || (rc = ensure(ctx, ctx->bY, yb)) || (rc = ensure(ctx, ctx->bTheta, tb)) ||
@@ -725,11 +821,17 @@ int gpl_lml_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const doub
     return GPL_OK;
 }
 
-// Per-kernel device time of the last lockstep call made with option "profile_events" = 1: ms[0..2] = total time in the
-// diag / potrf / below kernels, launches[0..2] = their launch counts.  Not part of the public header (bench.py only).
-int gpl_debug_last_timing(gpl_ctx *ctx, double *ms, int *launches) {
-    if (!ctx || !ms || !launches) return GPL_ERR_ARG;
-    for (int k = 0; k < 3; ++k) ms[k] = ctx->lk_ms[k], launches[k] = ctx->lk_launches[k];
+// Per-phase device time of the last instrumented call (option "profile_events" = 1): the optional stats struct of
+// SURVEY.md section 5.  Phases of gpl_lml_batched(_dev): 0 lk_diag, 1 lk_potrf_warp, 2 lk_below, 3 lk_winv, 4 lk_minv,
+// 5 lk_alpha, 6 lk_gradc + lk_gradsum.  gpl_lml_large: 0 covariance build, 1 factorisation + forward solve.
+int gpl_last_timing(gpl_ctx *ctx, gpl_timing *out) {
+    if (!ctx || !out) return fail(ctx, GPL_ERR_ARG, "gpl_last_timing: null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    out->n_phases = 7;
+    for (int k = 0; k < 8; ++k) {
+        out->ms[k] = k < 7 ? ctx->lk_ms[k] : 0.0;
+        out->launches[k] = k < 7 ? ctx->lk_launches[k] : 0;
+    }
     return GPL_OK;
 }
 
@@ -755,7 +857,14 @@ int gpl_debug_phase_profile(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, co
 // ---- posterior ---------------------------------------------------------------------------------------------------
 static void posterior_release(gpl_post *post) {  // caller holds the context lock (or there is no context)
     gpl_ctx *ctx = post->ctx;
-    if (ctx) cudaSetDevice(ctx->device);
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        for (size_t k = 0; k < ctx->livePosts.size(); ++k)
+            if (ctx->livePosts[k] == post) {
+                ctx->livePosts.erase(ctx->livePosts.begin() + k);
+                break;
+            }
+    }
     if (post->block) {
         if (ctx && ctx->postFree.size() < 8) {
             cudaStreamSynchronize(ctx->stream);  // nothing in flight reads it any more
@@ -882,6 +991,7 @@ int gpl_posterior_fit(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const do
     if (!X || !y || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_posterior_fit: null pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, ctx->stream);
     gpl_post *post = new (std::nothrow) gpl_post();
     if (!post) return fail(ctx, GPL_ERR_ARG, "out of host memory");
     rc = posterior_fit_impl(ctx, prog, n, d, X, y, theta, p, sigma2, jitter, post);
@@ -890,6 +1000,7 @@ int gpl_posterior_fit(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const do
         posterior_release(post);
         return rc;
     }
+    ctx->livePosts.push_back(post);
     *out = post;
     return GPL_OK;
 }
@@ -903,8 +1014,10 @@ int gpl_posterior_logpdf(gpl_post *post, double *lml) {
 int gpl_posterior_alpha(gpl_post *post, double *alpha) {
     if (!post || !alpha) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_alpha: null argument");
     gpl_ctx *ctx = post->ctx;
+    if (!ctx) return fail(nullptr, GPL_ERR_ARG, "posterior handle outlived its context (gpl_destroy was called)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, ctx->stream);
     CU(ctx, cudaMemcpyAsync(alpha, post->alpha + (size_t)post->nt * TS, (size_t)post->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
@@ -913,8 +1026,10 @@ int gpl_posterior_alpha(gpl_post *post, double *alpha) {
 int gpl_posterior_factor(gpl_post *post, double *U) {
     if (!post || !U) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_factor: null argument");
     gpl_ctx *ctx = post->ctx;
+    if (!ctx) return fail(nullptr, GPL_ERR_ARG, "posterior handle outlived its context (gpl_destroy was called)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, ctx->stream);
     const int n = post->n, nt = post->nt;
     int rc = ensure(ctx, ctx->bK, (size_t)n * n * 8);
     if (rc) return rc;
@@ -930,9 +1045,11 @@ int gpl_posterior_factor(gpl_post *post, double *U) {
 int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean, double *var) {
     if (!post || !Xs || !mean || m <= 0) return fail(nullptr, GPL_ERR_ARG, "gpl_posterior_mean_var: bad argument");
     gpl_ctx *ctx = post->ctx;
+    if (!ctx) return fail(nullptr, GPL_ERR_ARG, "posterior handle outlived its context (gpl_destroy was called)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     const int nt = post->nt, d = post->d;
     const size_t smem = predict_smem_bytes();
     bool &attr_set = ctx->attr_pred;
@@ -1012,39 +1129,31 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
-    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16;
-    if (per_item * (size_t)B > ctx->lk_ws_limit)
-        return fail(ctx, GPL_ERR_LIMIT, "gpl_predict_batched: %d rows of n=%d exceed the factor workspace cap; split the chain", B, n);
+    // rows per pass: the factor workspace cap ("lk_ws_limit_mb") bounds how many posteriors are resident at once; longer
+    // chains run in passes of Bc rows (same bits as in one piece: every row is independent)
+    const size_t per_item = (size_t)ntri * TILE_BYTES + (size_t)nt * DSIZE * 8 + (size_t)nt * TS * 8 + 16 +
+                            (size_t)nt * TILE_BYTES + (size_t)nt * TS * 8;
+    int Bc = (int)(ctx->lk_ws_limit / per_item);
+    Bc = Bc < 1 ? 1 : (Bc > B ? B : Bc);
     const size_t tb = (size_t)(p > 0 ? p : 1) * B * 8, sb = (size_t)(sigma2_batched ? B : 1) * 8;
     if ((rc = ensure(ctx, ctx->bX, (size_t)n * d * 8)) || (rc = ensure(ctx, ctx->bY, (size_t)n * 8)) ||
         (rc = ensure(ctx, ctx->bTheta, tb)) || (rc = ensure(ctx, ctx->bSigma, sb)) || (rc = ensure(ctx, ctx->bLml, (size_t)B * 8)) ||
         (rc = ensure(ctx, ctx->bInfo, (size_t)B * 4)) || (rc = ensure(ctx, ctx->bXs, (size_t)m * d * 8)) ||
         (rc = ensure(ctx, ctx->bMean, (size_t)m * B * 8)) || (rc = ensure(ctx, ctx->bVar, (size_t)m * B * 8)) ||
-        (rc = ensure(ctx, ctx->lkW, (size_t)B * nt * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkAlpha, (size_t)B * nt * TS * 8)))
+        (rc = ensure(ctx, ctx->lkW, (size_t)Bc * nt * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkAlpha, (size_t)Bc * nt * TS * 8)))
         return rc;
     CU(ctx, cudaMemcpyAsync(ctx->bX.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->bY.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (p > 0) CU(ctx, cudaMemcpyAsync(ctx->bTheta.p, Theta, (size_t)p * B * 8, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->bSigma.p, sigma2, sb, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->bXs.p, Xs, (size_t)m * d * 8, cudaMemcpyHostToDevice, st));
-    rc = launch_lml_lockstep(ctx, prog->dev, n, d, ptr<double>(ctx->bX), 0, ptr<double>(ctx->bY), 0, ptr<double>(ctx->bTheta), p,
-                             ptr<double>(ctx->bSigma), sigma2_batched, jitter, B, ptr<double>(ctx->bLml), ptr<int>(ctx->bInfo), st);
-    if (rc) return rc;
     if (!ctx->attr_post) {
         CU(ctx, cudaFuncSetAttribute(lk_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_post_smem_bytes()));
         ctx->attr_post = true;
     }
-    LkPostParams pq;
-    pq.nt = nt;
-    pq.tiles = ptr<double>(ctx->lkTiles);
-    pq.dblk = ptr<double>(ctx->lkD);
-    pq.z = ptr<double>(ctx->lkZ);
-    pq.winv = ptr<double>(ctx->lkW);
-    pq.alpha = ptr<double>(ctx->lkAlpha);
-    lk_post_kernel<<<B, NTHREADS, lk_post_smem_bytes(), st>>>(pq);
-    ctx->launches++;
     const size_t smem = predict_smem_bytes();
     if (!ctx->attr_pred) {
         CU(ctx, cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1055,50 +1164,67 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
     int occ = 0;
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, predict_kernel, NTHREADS, smem));
     if (occ < 1) return fail(ctx, GPL_ERR_CUDA, "predict kernel does not fit on an SM");
-    int nb_blocks = 8;
-    {
-        long long best = -1;
-        for (int nb : {8, 6, 4}) {
-            const long long units = (long long)B * ((m + 8 * nb - 1) / (8 * nb));
-            const long long cost = ((units + ctx->sm_count - 1) / ctx->sm_count) * nb;
-            if (best < 0 || cost < best) {
-                best = cost;
-                nb_blocks = nb;
+    for (int off = 0; off < B; off += Bc) {
+        const int nb = (B - off < Bc) ? B - off : Bc;
+        const size_t s_off = sigma2_batched ? (size_t)off : 0;
+        rc = launch_lml_lockstep(ctx, prog->dev, n, d, ptr<double>(ctx->bX), 0, ptr<double>(ctx->bY), 0,
+                                 ptr<double>(ctx->bTheta) + (size_t)off * p, p, ptr<double>(ctx->bSigma) + s_off, sigma2_batched,
+                                 jitter, nb, ptr<double>(ctx->bLml) + off, ptr<int>(ctx->bInfo) + off, st);
+        if (rc) return rc;
+        LkPostParams pq;
+        pq.nt = nt;
+        pq.tiles = ptr<double>(ctx->lkTiles);
+        pq.dblk = ptr<double>(ctx->lkD);
+        pq.z = ptr<double>(ctx->lkZ);
+        pq.winv = ptr<double>(ctx->lkW);
+        pq.alpha = ptr<double>(ctx->lkAlpha);
+        lk_post_kernel<<<nb, NTHREADS, lk_post_smem_bytes(), st>>>(pq);
+        ctx->launches++;
+        int nb_blocks = 8;
+        {
+            long long best = -1;
+            for (int w : {8, 6, 4}) {
+                const long long units = (long long)nb * ((m + 8 * w - 1) / (8 * w));
+                const long long cost = ((units + ctx->sm_count - 1) / ctx->sm_count) * w;
+                if (best < 0 || cost < best) {
+                    best = cost;
+                    nb_blocks = w;
+                }
             }
         }
+        const long long units = (long long)nb * ((m + 8 * nb_blocks - 1) / (8 * nb_blocks));
+        int grid = ctx->sm_count * occ;
+        if (grid > units) grid = (int)units;
+        if ((rc = ensure(ctx, ctx->bWsV, (size_t)grid * nt * TILE_BYTES))) return rc;
+        PredictParams prm;
+        prm.prog = prog->dev;
+        prm.n = n;
+        prm.nt = nt;
+        prm.d = d;
+        prm.p = p;
+        prm.m = m;
+        prm.want_var = var != nullptr;
+        prm.items = nb;
+        prm.theta_stride = p;
+        prm.tiles_stride = ntri * TILE_ELEMS;
+        prm.winv_stride = (long long)nt * TILE_ELEMS;
+        prm.alpha_stride = (long long)nt * TS;
+        prm.info = ptr<int>(ctx->bInfo) + off;
+        prm.X = ptr<double>(ctx->bX);
+        prm.theta = ptr<double>(ctx->bTheta) + (size_t)off * p;
+        prm.Xs = ptr<double>(ctx->bXs);
+        prm.tiles = ptr<double>(ctx->lkTiles);
+        prm.winv = ptr<double>(ctx->lkW);
+        prm.alpha = ptr<double>(ctx->lkAlpha);
+        prm.wsV = ptr<double>(ctx->bWsV);
+        prm.mean = ptr<double>(ctx->bMean) + (size_t)off * m;
+        prm.var = ptr<double>(ctx->bVar) + (size_t)off * m;
+        if (nb_blocks == 8) predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+        else if (nb_blocks == 6) predict_kernel_nb6<<<grid, NTHREADS, smem, st>>>(prm);
+        else predict_kernel_nb4<<<grid, NTHREADS, smem, st>>>(prm);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
     }
-    const long long units = (long long)B * ((m + 8 * nb_blocks - 1) / (8 * nb_blocks));
-    int grid = ctx->sm_count * occ;
-    if (grid > units) grid = (int)units;
-    if ((rc = ensure(ctx, ctx->bWsV, (size_t)grid * nt * TILE_BYTES))) return rc;
-    PredictParams prm;
-    prm.prog = prog->dev;
-    prm.n = n;
-    prm.nt = nt;
-    prm.d = d;
-    prm.p = p;
-    prm.m = m;
-    prm.want_var = var != nullptr;
-    prm.items = B;
-    prm.theta_stride = p;
-    prm.tiles_stride = ntri * TILE_ELEMS;
-    prm.winv_stride = (long long)nt * TILE_ELEMS;
-    prm.alpha_stride = (long long)nt * TS;
-    prm.info = ptr<int>(ctx->bInfo);
-    prm.X = ptr<double>(ctx->bX);
-    prm.theta = ptr<double>(ctx->bTheta);
-    prm.Xs = ptr<double>(ctx->bXs);
-    prm.tiles = ptr<double>(ctx->lkTiles);
-    prm.winv = ptr<double>(ctx->lkW);
-    prm.alpha = ptr<double>(ctx->lkAlpha);
-    prm.wsV = ptr<double>(ctx->bWsV);
-    prm.mean = ptr<double>(ctx->bMean);
-    prm.var = ptr<double>(ctx->bVar);
-    if (nb_blocks == 8) predict_kernel<<<grid, NTHREADS, smem, st>>>(prm);
-    else if (nb_blocks == 6) predict_kernel_nb6<<<grid, NTHREADS, smem, st>>>(prm);
-    else predict_kernel_nb4<<<grid, NTHREADS, smem, st>>>(prm);
-    ctx->launches++;
-    CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(mean, ctx->bMean.p, (size_t)m * B * 8, cudaMemcpyDeviceToHost, st));
     if (var) CU(ctx, cudaMemcpyAsync(var, ctx->bVar.p, (size_t)m * B * 8, cudaMemcpyDeviceToHost, st));
     if (lml) CU(ctx, cudaMemcpyAsync(lml, ctx->bLml.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
@@ -1116,6 +1242,7 @@ int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X
     if (!X || (p > 0 && !theta)) return fail(ctx, GPL_ERR_ARG, "gpl_sample: null pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, ctx->stream);
     gpl_post *post = new (std::nothrow) gpl_post();
     if (!post) return fail(ctx, GPL_ERR_ARG, "out of host memory");
     double *zeros = new (std::nothrow) double[n]();
@@ -1141,11 +1268,8 @@ int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X
 }
 
 // ---- large-n ---------------------------------------------------------------------------------------------------------
-int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo, void *stream) {
-    if (!ctx || !dA || !dlogdet || !dinfo || n <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_chol_logdet_dev: bad argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+static int chol_logdet_dev_locked(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo,
+                                  cudaStream_t st) {
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     int rc;
@@ -1168,26 +1292,32 @@ int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double
     return GPL_OK;
 }
 
+int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo, void *stream) {
+    if (!ctx || !dA || !dlogdet || !dinfo || n <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_chol_logdet_dev: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    WsOrder order(ctx, (cudaStream_t)stream);
+    return chol_logdet_dev_locked(ctx, n, dA, want_factor, dlogdet, dinfo, (cudaStream_t)stream);
+}
+
 int gpl_chol_logdet(gpl_ctx *ctx, int n, double *A, int want_factor, double *logdet, int *info) {
     if (!ctx || !A || !logdet || n <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_chol_logdet: bad argument");
-    int rc;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        CU(ctx, cudaSetDevice(ctx->device));
-        if ((rc = ensure(ctx, ctx->bK, (size_t)n * n * 8)) || (rc = ensure(ctx, ctx->bLml, 16)) ||
-            (rc = ensure(ctx, ctx->bInfo, 4)))
-            return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->bK.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    rc = gpl_chol_logdet_dev(ctx, n, ptr<double>(ctx->bK), want_factor, ptr<double>(ctx->bLml), ptr<int>(ctx->bInfo),
-                             ctx->stream);
-    if (rc) return rc;
+    // one critical section from the upload to the download: the staging buffer bK belongs to this call throughout
     std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
+    int rc;
+    if ((rc = ensure(ctx, ctx->bK, (size_t)n * n * 8)) || (rc = ensure(ctx, ctx->bLml, 16)) || (rc = ensure(ctx, ctx->bInfo, 4)))
+        return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->bK.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = chol_logdet_dev_locked(ctx, n, ptr<double>(ctx->bK), want_factor, ptr<double>(ctx->bLml), ptr<int>(ctx->bInfo), st)))
+        return rc;
     int h_info = 0;
-    CU(ctx, cudaMemcpyAsync(logdet, ctx->bLml.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(&h_info, ctx->bInfo.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (want_factor) CU(ctx, cudaMemcpyAsync(A, ctx->bK.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpyAsync(logdet, ctx->bLml.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(&h_info, ctx->bInfo.p, 4, cudaMemcpyDeviceToHost, st));
+    if (want_factor) CU(ctx, cudaMemcpyAsync(A, ctx->bK.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
     if (info) *info = h_info;
     if (h_info) *logdet = NAN;
     return GPL_OK;
@@ -1201,6 +1331,7 @@ int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     if ((rc = ensure(ctx, ctx->ws, (size_t)(ntri + nt) * TILE_BYTES)) || (rc = ensure(ctx, ctx->bMisc, 64 + (size_t)nt * TS * 8)) ||

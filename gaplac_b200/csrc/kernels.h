@@ -61,6 +61,34 @@ __global__ void lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm);
 size_t lk_potrf_warp_smem_bytes();
 int lk_potrf_warp_items_per_cta();
 
+// ---- analytic gradient on the lockstep schedule (lml_grad_lockstep.cu) -----------------------------------------------
+// After the lockstep factorisation of a batch (L tiles, block inverses, z in the workspace) the gradient phases run as
+// batch-wide launches as well: W_jj = L_jj^-1 for every diagonal tile, M = L^-1 tile row by tile row, alpha = M' z,
+// then K^-1 = M' M tile by tile contracted on the fly with dK/dtheta.  M is stored as TRANSPOSED tiles in column-major
+// tile order (tile (k, j) at col_index(nt, k, j)) so that every operand stream of these phases is one contiguous run.
+__host__ __device__ inline long long col_index(int nt, int k, int j) { return (long long)j * nt - (long long)j * (j - 1) / 2 + (k - j); }
+struct LkGradParams {
+    DevProgram prog;
+    int n, d, nt, p, i;  // i: tile row of the current lk_minv launch
+    long long x_stride;
+    const double *X, *Theta;
+    const double *tiles, *dblk, *z;  // factor workspace of the lockstep schedule
+    double *winv;                    // B x nt tiles: W_jj
+    double *minv;                    // B x ntri tiles: (M_kj)' at col_index(nt, k, j)
+    double *alpha;                   // B x nt*64: alpha = K^-1 y
+    double *gpart;                   // B x ntri x p: per-tile partial sums of sum_ij W_ij dK_ij/dtheta
+    double *dtheta, *dy;             // outputs (dy may be NULL)
+    const int *info;
+    int B;
+};
+__global__ void lk_winv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * nt
+__global__ void lk_minv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * i  (row i, tiles j < i)
+__global__ void lk_alpha_kernel(const __grid_constant__ LkGradParams prm);    // grid B * nt
+__global__ void lk_gradc_kernel(const __grid_constant__ LkGradParams prm);    // grid B * ntri
+__global__ void lk_gradsum_kernel(const __grid_constant__ LkGradParams prm);  // grid ceil(B / 128)
+size_t lk_winv_smem_bytes();
+size_t lk_grad_smem_bytes();
+
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
 struct CovParams {
     DevProgram prog;

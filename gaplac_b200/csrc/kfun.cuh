@@ -34,6 +34,9 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
             a = -1.0 / h;
             da = 1.0 / (h * h);
         }
+        // a length scale must be > 0 (ScaleTransform throws otherwise [upstream]): poison the item instead of letting a
+        // negative or zero proposal produce a plausible-looking kernel -> NaN covariance -> info = 1, lml = -Inf
+        if ((f.kind == F_SQEXP || f.kind == F_OU) && !(h > 0.0)) a = da = __longlong_as_double(0x7ff8000000000000LL);
         if (f.kind == F_PARAM) {  // d term / d theta_f = (coef * the term's other per-item scalars) * product of its leaves
             int t = 0;
             while (tid >= P.term_begin[t + 1]) ++t;
@@ -287,11 +290,13 @@ __device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const It
 //   per-item scalar factor f (variance, Constant):  da_f * sum w prod_leaves k
 //   SqExp / OU length scale:                         tc * da_f * sum w (prod_leaves k) d^2   (resp. |d|)
 //   Linear offset c:                                 tc * sum w prod_{leaves != f} k
-// gsum: shared-memory accumulators (GPL_MAX_THETA doubles); one atomicAdd per (term, factor with a slot, warp).
+// gsum: shared-memory accumulators, one row of GPL_MAX_THETA doubles PER WARP (the caller passes its warp's row and
+// adds the rows up in a fixed order afterwards): lane 0 adds the warp total, so the summation order - and with it every
+// bit of the gradient - is the same from run to run (shared atomics were not).
 __device__ __forceinline__ void grad_reduce_add(double part, double *dst) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(dst, part);
+    if ((threadIdx.x & 31) == 0) *dst += part;
 }
 __device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const ItemScalars &S,
                                                       const double *__restrict__ X, int ldx, int n, const int (&gi)[2],

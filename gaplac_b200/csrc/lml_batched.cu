@@ -75,7 +75,7 @@ struct __align__(16) LmlSmem {
     double ybuf[TS];
     double tmp16[16];
     double L16s[256];
-    double gsum[GPL_MAX_THETA];
+    double gsum[NWARPS * GPL_MAX_THETA];  // one row per warp (deterministic summation order)
     double red[NWARPS];
     double logdet;
     int item;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
             sm.logdet = 0.0;
             sm.info = 0;
         }
-        if (tid < GPL_MAX_THETA) sm.gsum[tid] = 0.0;
+        if (tid < NWARPS * GPL_MAX_THETA) sm.gsum[tid] = 0.0;
         __syncthreads();
         const int b = sm.item;
         if (b >= prm.B) {
@@ -373,11 +373,16 @@ __device__ __forceinline__ void lml_batched_body(const LmlParams &prm) {
 #pragma unroll
                     for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = sym * (acc[mb][cc] - wsAl[gi[mb]] * wsAl[gj[cc]]);
                 __syncthreads();  // the tiles in S / Bt are consumed: S parks the weights
-                contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum);
+                contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA);
             }
         }
         __syncthreads();
-        if (tid < prm.p) prm.dtheta[(size_t)b * prm.p + tid] = info ? NAN : -0.5 * sm.gsum[tid];
+        if (tid < prm.p) {
+            double g = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) g += sm.gsum[w * GPL_MAX_THETA + tid];
+            prm.dtheta[(size_t)b * prm.p + tid] = info ? NAN : -0.5 * g;
+        }
         }  // GRAD
     }
 }

@@ -41,7 +41,7 @@ def gather_lml(local, B: int, group=None):
 
 def sharded_logpdf(ctx, prog, X, Y, Theta, sigma2, jitter: float = 0.0, group=None):
     """Evaluate this rank's block of a (B, p) hyperparameter batch on its own GPU and gather the B log-densities.
-    Y: (n,) shared or (B, n); sigma2: scalar or (B,).  Returns (lml[B], info[B]) as NumPy arrays on every rank."""
+    X: (n, d) shared or (B, n, d); Y: (n,) shared or (B, n); sigma2: scalar or (B,).  Returns (lml[B], info[B]) as NumPy arrays on every rank."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -52,8 +52,10 @@ def sharded_logpdf(ctx, prog, X, Y, Theta, sigma2, jitter: float = 0.0, group=No
     Yl = Yl[lo:hi] if Yl.ndim == 2 else Yl
     s2 = np.atleast_1d(np.asarray(sigma2, dtype=np.float64))
     s2 = s2[lo:hi] if s2.size > 1 else s2
+    Xl = np.asarray(X)
+    Xl = Xl[lo:hi] if Xl.ndim == 3 else Xl          # per-item inputs (B, n, d) are sharded like Theta
     if hi > lo:
-        lml, info = ctx.lml_batched(prog, X, Yl, Theta[lo:hi], s2, jitter)
+        lml, info = ctx.lml_batched(prog, Xl, Yl, Theta[lo:hi], s2, jitter)
     else:
         lml, info = np.empty(0), np.empty(0, dtype=np.int32)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")

@@ -99,3 +99,37 @@ def make_c5(seed: int = 5, n: int = 8192):
     x = rng.uniform(-50, 50, n)
     y = rng.standard_normal(n)
     return dict(X=x.reshape(-1, 1), y=y, theta=np.array([1.0, 0.1]), sigma2=0.0, ops=prog_c5())
+
+
+# ---- the reference's legacy fixtures (tests/golden/, extracted by tools/make_golden.py from test/testin/*.tsv) ----------
+GOLDEN_JITTER = 1e-9
+
+
+def prog_golden(tag: str = "3206"):
+    """Cat(PersonID)*Cat(StoolPairs) + Cat(PersonID) + Linear(nutrient) [+ Noise], one variance slot per term
+    (generating command test/pred.jl:22).  X columns = [PersonID, StoolPairs, nutrient]."""
+    ops = [Op(CAT, col=0), Op(CAT, col=1), Op(MUL, var_slot=0), Op(CAT, col=0, var_slot=1), Op(ADD),
+           Op(LINEAR, col=2, value=0.0, var_slot=2), Op(ADD)]
+    if tag == "3206":
+        ops += [Op(NOISE, var_slot=3), Op(ADD)]
+    return ops
+
+
+def make_golden(golden_dir: str, tag: str = "3206"):
+    """X (n x 3), y (bug), Theta (chain rows x p), sigma2 (rows), and the fixture's own answers: lml = l_pi - legacy prior."""
+    import csv
+    import os
+    with open(os.path.join(golden_dir, f"input_pair_{tag}.csv")) as f:
+        rows = list(csv.DictReader(f))
+    X = np.array([[float(r["PersonID"]), float(r["StoolPairs"]), float(r["nutrient"])] for r in rows])
+    y = np.array([float(r["bug"]) for r in rows])
+    with open(os.path.join(golden_dir, f"mcmc_{tag}.csv")) as f:
+        chain = [{k: float(v) for k, v in r.items()} for r in csv.DictReader(f)]
+    names = ("var1", "var2", "var3", "var4") if tag == "3206" else ("var1", "var2", "var3")
+    Theta = np.array([[c[k] for k in names] for c in chain])
+    sigma2 = np.zeros(len(chain)) if tag == "3206" else np.array([c["eta"] ** 2 for c in chain])
+    prior = np.array([sum(2 * np.log(2.0) + 2 * np.log(c[k]) - 2 * c[k] for k in names) for c in chain])
+    if tag != "3206":
+        prior = prior + np.array([np.log(c["eta"]) - c["eta"] + 0.5 * np.log(2 * np.pi) for c in chain])
+    lml_known = np.array([c["lpi"] for c in chain]) - prior
+    return dict(X=X, y=y, Theta=Theta, sigma2=sigma2, jitter=GOLDEN_JITTER, lml_known=lml_known, ops=prog_golden(tag))

@@ -46,7 +46,10 @@ typedef enum gpl_status {
  * operations of src/gp_parts.jl:55,59 (`+` -> :add, `*` -> :multiply). */
 typedef enum gpl_kind {
     GPL_SQEXP = 0,    /* exp(-(x-x')^2 / (2 l^2))      hyperparameter l (> 0) */
-    GPL_OU = 1,       /* exp(-|x-x'| / l)               hyperparameter l (> 0) */
+    GPL_OU = 1,       /* exp(-|x-x'| / l)               hyperparameter l (> 0).  A FIXED l <= 0 is rejected by
+                         gpl_program_create; an l <= 0 (or NaN) arriving through a theta slot makes that item's covariance
+                         NaN: info[b] = 1, lml[b] = -Inf, NaN gradient / predictions (the reference's ScaleTransform
+                         throws for l <= 0 [upstream]; a sampler sees a rejected proposal) */
     GPL_LINEAR = 2,   /* x x' + c                       hyperparameter c */
     GPL_CAT = 3,      /* x == x' ? 1 : 0                none */
     GPL_CONSTANT = 4, /* c                              hyperparameter c */
@@ -79,16 +82,38 @@ typedef struct gpl_prog gpl_prog; /* compiled kernel-program */
 typedef struct gpl_post gpl_post; /* posterior: Cholesky factor and alpha resident in HBM */
 
 /* ---- context ------------------------------------------------------------------------------------- */
-/* device = CUDA ordinal, or -1 for the current device.  Calls on one context serialise on its stream. */
+/* device = CUDA ordinal, or -1 for the current device.  Host entry points on one context serialise (mutex + the
+ * context's stream).  The *_dev entry points enqueue on the CALLER's stream and return; the context owns one workspace,
+ * so every call first makes its stream wait (cudaStreamWaitEvent) for the previous call that used the workspace, on
+ * whatever stream that was: calls on one context never overlap on the device, they only pipeline.  Use one context per
+ * concurrent chain for real concurrency.  gpl_destroy synchronises the device, releases the device memory of any
+ * posterior still alive and detaches it: gpl_posterior_free on such a handle is still valid (and required), every other
+ * call on it returns GPL_ERR_ARG. */
 int gpl_init(int device, gpl_ctx **out);
 int gpl_destroy(gpl_ctx *ctx);
+/* Run the host entry points of this context on the caller's CUDA stream (cudaStream_t as void*) instead of the
+ * context's own one; NULL restores it.  The calls stay blocking; a host that records CUDA events on its stream (or
+ * orders other work on it, e.g. CUDA.jl's task stream) then sees the library's copies and kernels in that order. */
+int gpl_set_stream(gpl_ctx *ctx, void *stream);
 const char *gpl_last_error(gpl_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
 int gpl_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
- * per-item kernel, 2 lockstep with the one-CTA-per-item potrf kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap) */
+ * per-item kernel, 2 lockstep with the one-CTA-per-item potrf kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
+ * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);
+/* Optional per-call statistics.  With option "profile_events" = 1 the library brackets every
+ * kernel launch of gpl_lml_batched(_dev) / gpl_lml_large with CUDA events (and synchronises the stream at the end of the
+ * call); gpl_last_timing returns the device time per phase of the last such call.  Phases of the batched calls:
+ * 0 lk_diag, 1 lk_potrf_warp, 2 lk_below (factorisation), 3 lk_winv, 4 lk_minv, 5 lk_alpha, 6 lk_gradc (gradient);
+ * gpl_lml_large: 0 covariance build, 1 factorisation + forward solve. */
+typedef struct gpl_timing {
+    int32_t n_phases;
+    int32_t launches[8];
+    double ms[8];
+} gpl_timing;
+int gpl_last_timing(gpl_ctx *ctx, gpl_timing *out);
 /* device facts for reports: name (<= len bytes), SM count, SM clock kHz */
 int gpl_device_info(gpl_ctx *ctx, char *name, int len, int *sm_count, int *clock_khz);
 
@@ -143,8 +168,8 @@ int gpl_posterior_mean_var(gpl_post *post, int m, const double *Xs, double *mean
  * (src/plotting.jl:6-12 per row; commands stubbed at CLI/src/main.jl:8-16, output columns test/pred.jl:11-14).
  * X (n x d) and y (n) are shared by the rows.  mean, var: m x B column-major (row b at b*m; var may be NULL);
  * lml (B, optional) and info (B, optional) as in gpl_lml_batched: a row whose covariance is not positive
- * definite has info[b] != 0, lml[b] = -Inf and NaN predictions.  All rows are factored in one batch; returns
- * GPL_ERR_LIMIT when B rows of size n exceed the factor workspace cap ("lk_ws_limit_mb"): split the chain. */
+ * definite has info[b] != 0, lml[b] = -Inf and NaN predictions.  The rows are factored in lockstep batches of as many
+ * rows as the factor workspace cap ("lk_ws_limit_mb") holds; longer chains run in several passes inside the call. */
 int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
                         const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter, int B,
                         int m, const double *Xs, double *mean, double *var, double *lml, int *info);

@@ -49,6 +49,28 @@ def test_harmonic_evidence_is_stable_where_the_naive_form_overflows():
     assert abs(G.log_bayes_factor(ll, ll2) - 3.0 / np.log(10.0)) < 1e-12
 
 
+def test_select_chains_reproduces_the_reference_base2_harmonic_mean():
+    """CLI/src/select.jl:15-20: lp_k = log2(harmmean(BigFloat(2) .^ lp)), Bayes = lp1 - lp2 - evaluated here in 60-digit
+    arithmetic exactly as written there, against the stable float64 form."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 60
+    rng = np.random.default_rng(0)
+    lp1 = -939.0 + rng.normal(0, 2.0, 100)
+    lp2 = -640.0 + rng.normal(0, 1.5, 100)
+
+    def ref(lp):
+        v = [mp.mpf(2) ** mp.mpf(float(x)) for x in lp]
+        hm = len(v) / sum(1 / x for x in v)
+        return mp.log(hm, 2)
+
+    assert abs(G.log2_harmmean_exp2(lp1) - float(ref(lp1))) < 1e-12 * abs(float(ref(lp1)))
+    bayes = mp.log(mp.mpf(2) ** ref(lp1) / mp.mpf(2) ** ref(lp2), 2)
+    assert abs(G.select_chains_log2_bayes(lp1, lp2) - float(bayes)) < 1e-10
+    const = np.full(7, -12.5)
+    assert G.select_chains_log2_bayes(const, const - 2.0) == pytest.approx(2.0, abs=1e-13)   # constant chains: c1 - c2
+    assert G.select_formulae_log2_bayes(-31.53397005887427, -35.97395926954643) == pytest.approx(4.44, abs=5e-3)  # README.md:111-117
+
+
 @pytest.mark.gpu
 def test_predict_chain_golden_model_matches_oracle():
     """`predict ... --mcmc mcmc_3206.tsv --at "nutrient=-5:0.5:5;PersonID=0;StoolPairs=0"` (test/pred.jl:22): per-row

@@ -86,7 +86,7 @@ def test_lml_batched_workspace_chunking_is_invisible(ctx):
     try:
         parts, info2 = ctx.lml_batched(prog, d["X"], d["Y"], d["Theta"], 0.0)
     finally:
-        ctx.set_option("lk_ws_limit_mb", 12 * 1024)
+        ctx.set_option("lk_ws_limit_mb", 24 * 1024)
     assert np.array_equal(whole, parts) and np.array_equal(info, info2)
 
 
@@ -318,3 +318,43 @@ def test_lml_large_matches_oracle(ctx):
     ref, rinfo = CO.lml(d["ops"], d["X"], d["y"], d["theta"], 0.0)
     assert info == 0 and rinfo == 0
     assert abs(lml - ref) < LML_RTOL * abs(ref)
+
+
+# ---------------------------------------------------------------------------------------------- handle lifetimes
+def test_posterior_outliving_its_context_is_detached_not_dangling():
+    """gpl_destroy with a live posterior: the device block goes with the context, the handle stays valid for
+    gpl_posterior_free and every other call on it fails cleanly (no use-after-free)."""
+    c = _lib.Context(0)
+    X, y = _data(80, seed=1)
+    prog = c.program(ALL_KINDS)
+    post = c.posterior_fit(prog, X, y, THETA, 0.1)
+    keep = post.logpdf()
+    c.close()
+    assert post.logpdf() == keep                      # host-side value
+    with pytest.raises(_lib.GaplacError):
+        post.alpha()
+    with pytest.raises(_lib.GaplacError):
+        post.mean_and_var(X[:5])
+    post.free()
+    post.free()                                       # idempotent
+
+
+def test_predict_batched_runs_in_passes_beyond_the_workspace_cap(ctx):
+    """More chain rows than the factor workspace holds: several passes inside the call, same bits."""
+    X, y = _data(200, seed=9)
+    prog = ctx.program(ALL_KINDS)
+    rng = np.random.default_rng(1)
+    Th = THETA[None, :] * rng.uniform(0.8, 1.2, (40, 5))
+    Xs, _ = _data(70, seed=11)
+    whole = ctx.predict_batched(prog, X, y, Th, 0.1, Xs)
+    ctx.set_option("lk_ws_limit_mb", 6)               # 10 tiles + 4 inverses per row: ~ 12 rows per pass
+    try:
+        parts = ctx.predict_batched(prog, X, y, Th, 0.1, Xs)
+    finally:
+        ctx.set_option("lk_ws_limit_mb", 24 * 1024)
+    for a, b in zip(whole, parts):
+        assert np.array_equal(a, b)
+    U, alpha = CO.posterior(ALL_KINDS, X, y, Th[33], 0.1)
+    rm, rv = CO.mean_and_var(ALL_KINDS, X, U, alpha, Xs, Th[33])
+    assert np.max(np.abs(parts[0][33] - rm)) < PRED_TOL * max(1.0, np.max(np.abs(rm)))
+    assert np.max(np.abs(parts[1][33] - rv)) < PRED_TOL * max(1.0, np.max(np.abs(rv)))

@@ -28,7 +28,41 @@ class _OracleCtx:
 
     def lml_batched(self, prog, X, Y, Theta, sigma2, jitter=0.0):
         from oracle import c_oracle as CO
-        return CO.lml_batched(prog, X, Y, Theta, sigma2, jitter)
+        return CO.lml_batched(prog, X, Y, Theta, sigma2, jitter, x_batched=np.ndim(X) == 3)
+
+
+def _per_item_problem(B, n=24):
+    rng = np.random.default_rng(B)
+    d = W.make_c2(n=n, B=B)
+    Xb = rng.uniform(-5, 5, (B, n, 1))               # a different input set per item
+    Yb = rng.standard_normal((B, n))
+    return d["ops"], Xb, Yb, d["Theta"], rng.uniform(0.05, 0.2, B)
+
+
+def _worker_per_item(rank, world, port, B, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ops, Xb, Yb, Th, s2 = _per_item_problem(B)
+    lml, _ = shard.sharded_logpdf(_OracleCtx(), ops, Xb, Yb, Th, s2)
+    np.save(os.path.join(out_dir, f"lml_{rank}.npy"), lml)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_per_item_inputs(tmp_path):
+    """X (B, n, d), Y (B, n) and sigma2 (B,) are all sliced to the rank's block: rank 1 must read ITS items' X."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    B = 7
+    mp.spawn(_worker_per_item, args=(2, port, B, str(tmp_path)), nprocs=2, join=True)
+    from oracle import c_oracle as CO
+    ops, Xb, Yb, Th, s2 = _per_item_problem(B)
+    ref, _ = CO.lml_batched(ops, Xb, Yb, Th, s2, x_batched=True)
+    for rank in range(2):
+        assert np.array_equal(np.load(tmp_path / f"lml_{rank}.npy"), ref)
 
 
 def _worker(rank, world, port, B, out_dir):
