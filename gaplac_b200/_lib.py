@@ -24,7 +24,7 @@ SYMBOLS = [
     "gpl_cov", "gpl_cov_dev", "gpl_cross_cov", "gpl_lml_batched", "gpl_lml_batched_dev", "gpl_posterior_fit",
     "gpl_posterior_free", "gpl_posterior_logpdf", "gpl_posterior_alpha", "gpl_posterior_factor",
     "gpl_posterior_mean_var", "gpl_sample", "gpl_chol_logdet", "gpl_chol_logdet_dev", "gpl_lml_large",
-    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream",
+    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream", "gpl_mcmc_nuts",
 ]
 
 
@@ -81,6 +81,9 @@ def load() -> C.CDLL:
     lib.gpl_device_info.argtypes = [_vp, C.c_char_p, C.c_int, _ip, _ip]
     lib.gpl_last_timing.argtypes = [_vp, C.POINTER(GplTiming)]
     lib.gpl_set_stream.argtypes = [_vp, _vp]
+    lib.gpl_mcmc_nuts.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
+                                  C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.POINTER(C.c_longlong)]
     lib.gpl_program_create.argtypes = [_vp, C.POINTER(GplOp), C.c_int, C.POINTER(_vp)]
     lib.gpl_program_destroy.argtypes = [_vp]
     lib.gpl_program_n_theta.argtypes = [_vp]

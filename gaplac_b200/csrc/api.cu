@@ -1233,6 +1233,180 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
     return GPL_OK;
 }
 
+// ---- batched on-device sampler ---------------------------------------------------------------------------------------
+int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, int x_batched, const double *Y,
+                  int y_batched, int p, const double *lo, const double *hi, const double *sigma2, int sigma2_batched,
+                  double jitter, int B, const double *q0, const gpl_mcmc_opts *opts, double *theta, double *lp, double *q,
+                  double *accept, double *eps, int *depth, int *n_leapfrog, int *divergent, int *status,
+                  long long *n_grad_evals) {
+    int rc = check_prog_args(ctx, prog, n, d, p);
+    if (rc) return rc;
+    if (!opts || !X || !Y || !sigma2 || !q0 || !theta || !lp || B <= 0 || (p > 0 && (!lo || !hi)))
+        return fail(ctx, GPL_ERR_ARG, "gpl_mcmc_nuts: null pointer or B <= 0");
+    if (p > MC_MAX_P) return fail(ctx, GPL_ERR_LIMIT, "gpl_mcmc_nuts: p=%d exceeds %d", p, MC_MAX_P);
+    if (opts->n_samples <= 0) return fail(ctx, GPL_ERR_ARG, "gpl_mcmc_nuts: n_samples=%d", opts->n_samples);
+    for (int k = 0; k < p; ++k)
+        if (!(hi[k] > lo[k])) return fail(ctx, GPL_ERR_ARG, "gpl_mcmc_nuts: prior bounds of slot %d are not lo < hi", k);
+    McmcDevParams mp;
+    memset(&mp, 0, sizeof(mp));
+    McmcConfig &c = mp.cfg;
+    c.n = n;
+    c.p = p;
+    c.latent = opts->latent ? 1 : 0;
+    c.dim = p + (c.latent ? n : 0);
+    if (c.dim < 1) return fail(ctx, GPL_ERR_ARG, "gpl_mcmc_nuts: nothing to sample (p = 0 and latent = 0)");
+    c.max_depth = opts->max_depth > 0 ? opts->max_depth : MC_MAX_DEPTH;
+    if (c.max_depth > MC_MAX_DEPTH) return fail(ctx, GPL_ERR_LIMIT, "gpl_mcmc_nuts: max_depth %d exceeds %d", c.max_depth, MC_MAX_DEPTH);
+    c.n_samples = opts->n_samples;
+    c.n_adapt = opts->n_adapt >= 0 ? opts->n_adapt : (opts->n_samples / 2 < 1000 ? opts->n_samples / 2 : 1000);
+    c.search_eps = opts->search_eps ? 1 : 0;
+    c.adapt_mass = opts->adapt_mass ? 1 : 0;
+    c.record_warmup = opts->record_warmup ? 1 : 0;
+    c.record_q = q ? 1 : 0;
+    c.delta = opts->delta > 0 ? opts->delta : 0.65;
+    c.max_dh = opts->max_dh > 0 ? opts->max_dh : 1000.0;
+    c.obs_sd = opts->obs_sd > 0 ? opts->obs_sd : 1.0;
+    c.eps0 = opts->eps0 > 0 ? opts->eps0 : 0.1;
+    c.seed = opts->seed;
+    for (int k = 0; k < p; ++k) c.lo[k] = lo[k], c.hi[k] = hi[k];
+    mc_setup_windows(c);
+    const int T = c.n_adapt + c.n_samples, n_rec = c.n_samples + (c.record_warmup ? c.n_adapt : 0), dim = c.dim;
+    const int pp = p > 0 ? p : 1;
+
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    WsOrder order(ctx, st);
+    // one device block for everything the sampler owns (released before returning)
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t vec_stride = (size_t)mc_vectors_per_chain(c.max_depth) * dim;
+    const size_t xb = (size_t)n * d * (x_batched ? B : 1) * 8, yb = (size_t)n * (y_batched ? B : 1) * 8,
+                 sb = (size_t)(sigma2_batched ? B : 1) * 8;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += up(bytes);
+        return o;
+    };
+    const size_t o_state = take((size_t)B * mcmc_state_bytes()), o_vec = take((size_t)B * vec_stride * 8), o_q0 = take((size_t)B * dim * 8),
+                 o_x = take(xb), o_y = take(yb), o_s2 = take(sb), o_the = take((size_t)B * pp * 8), o_ye = take((size_t)B * n * 8),
+                 o_lml = take((size_t)B * 8), o_dth = take((size_t)B * pp * 8), o_dy = take((size_t)B * n * 8), o_info = take((size_t)B * 4),
+                 o_th = take((size_t)B * n_rec * pp * 8), o_lp = take((size_t)B * n_rec * 8), o_acc = take((size_t)B * n_rec * 8),
+                 o_eps = take((size_t)B * n_rec * 8), o_qo = take(q ? (size_t)B * n_rec * dim * 8 : 8), o_dep = take((size_t)B * n_rec * 4),
+                 o_nl = take((size_t)B * n_rec * 4), o_div = take((size_t)B * n_rec * 4), o_done = take(256), o_stat = take((size_t)B * 4);
+    char *blk = nullptr;
+    CU(ctx, cudaMalloc((void **)&blk, off));
+    struct Guard {  // frees the block (and the graph objects) on every exit path
+        char *p;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        ~Guard() {
+            if (ge) cudaGraphExecDestroy(ge);
+            if (g) cudaGraphDestroy(g);
+            cudaFree(p);
+        }
+    } guard{blk};
+    auto dptr = [&](size_t o) { return reinterpret_cast<double *>(blk + o); };
+    auto iptr = [&](size_t o) { return reinterpret_cast<int *>(blk + o); };
+    CU(ctx, cudaMemsetAsync(blk + o_done, 0, 256, st));
+    CU(ctx, cudaMemcpyAsync(blk + o_q0, q0, (size_t)B * dim * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(blk + o_x, X, xb, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(blk + o_y, Y, yb, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(blk + o_s2, sigma2, sb, cudaMemcpyHostToDevice, st));
+    mp.B = B;
+    mp.chain_offset = opts->chain_offset;
+    mp.n_rec = n_rec;
+    mp.state = reinterpret_cast<ChainState *>(blk + o_state);
+    mp.vec = dptr(o_vec);
+    mp.vec_stride = (long long)vec_stride;
+    mp.q0 = dptr(o_q0);
+    mp.Y = dptr(o_y);
+    mp.y_stride = y_batched ? n : 0;
+    mp.theta_eval = dptr(o_the);
+    mp.y_eval = dptr(o_ye);
+    mp.lml = dptr(o_lml);
+    mp.dtheta = dptr(o_dth);
+    mp.dy = dptr(o_dy);
+    mp.info = iptr(o_info);
+    mp.theta_out = dptr(o_th);
+    mp.lp_out = dptr(o_lp);
+    mp.accept_out = dptr(o_acc);
+    mp.eps_out = dptr(o_eps);
+    mp.q_out = q ? dptr(o_qo) : nullptr;
+    mp.depth_out = iptr(o_dep);
+    mp.nleap_out = iptr(o_nl);
+    mp.div_out = iptr(o_div);
+    mp.done = reinterpret_cast<unsigned int *>(blk + o_done);
+    const int warps_per_block = 4, grid = (B + warps_per_block - 1) / warps_per_block;
+    mcmc_init_kernel<<<grid, 32 * warps_per_block, 0, st>>>(mp);
+    ctx->launches++;
+    // one step: evaluate log-density + gradient at every chain's emitted point, then advance every chain
+    const int saved_profile = ctx->profile_events;
+    ctx->profile_events = 0;
+    auto step = [&]() -> int {
+        int r = launch_lml_lockstep(ctx, prog->dev, n, d, dptr(o_x), x_batched, c.latent ? dptr(o_ye) : dptr(o_y),
+                                    c.latent ? 1 : y_batched, dptr(o_the), p, dptr(o_s2), sigma2_batched, jitter, B, dptr(o_lml),
+                                    iptr(o_info), st, dptr(o_dth), dptr(o_dy), 1);
+        if (r) return r;
+        mcmc_advance_kernel<<<grid, 32 * warps_per_block, 0, st>>>(mp);
+        ctx->launches++;
+        return GPL_OK;
+    };
+    const uint64_t launches_before = ctx->launches;
+    rc = step();  // the first step also sizes the workspaces (no allocation may happen inside a capture)
+    const uint64_t launches_per_step = ctx->launches - launches_before;
+    long long steps = 1;
+    unsigned int done = 0;
+    if (rc == GPL_OK) {
+        // capture one step and replay it; the host only polls the done counter every `poll` steps
+        bool graph_ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (graph_ok) {
+            rc = step();
+            ctx->launches -= launches_per_step;  // captured, not launched
+            cudaError_t e = cudaStreamEndCapture(st, &guard.g);
+            graph_ok = rc == GPL_OK && e == cudaSuccess && guard.g &&
+                       cudaGraphInstantiate(&guard.ge, guard.g, 0) == cudaSuccess;
+            if (!graph_ok) {
+                cudaGetLastError();
+                rc = GPL_OK;
+            }
+        }
+        const long long max_steps = (long long)T * ((1LL << c.max_depth) + 1) + 64;
+        const int poll = 16;
+        while (rc == GPL_OK && done < (unsigned)B && steps < max_steps) {
+            for (int k = 0; k < poll && rc == GPL_OK; ++k) {
+                if (graph_ok) {
+                    if (cudaGraphLaunch(guard.ge, st) != cudaSuccess) rc = fail(ctx, GPL_ERR_CUDA, "gpl_mcmc_nuts: graph launch failed");
+                    ctx->launches += launches_per_step;
+                } else {
+                    rc = step();
+                }
+                ++steps;
+            }
+            if (rc) break;
+            CU(ctx, cudaMemcpyAsync(&done, mp.done, sizeof(done), cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+        }
+    }
+    ctx->profile_events = saved_profile;
+    if (rc) return rc;
+    mcmc_status_kernel<<<(B + 127) / 128, 128, 0, st>>>(mp.state, B, iptr(o_stat));
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    if (p > 0) CU(ctx, cudaMemcpyAsync(theta, blk + o_th, (size_t)B * n_rec * p * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(lp, blk + o_lp, (size_t)B * n_rec * 8, cudaMemcpyDeviceToHost, st));
+    if (q) CU(ctx, cudaMemcpyAsync(q, blk + o_qo, (size_t)B * n_rec * dim * 8, cudaMemcpyDeviceToHost, st));
+    if (accept) CU(ctx, cudaMemcpyAsync(accept, blk + o_acc, (size_t)B * n_rec * 8, cudaMemcpyDeviceToHost, st));
+    if (eps) CU(ctx, cudaMemcpyAsync(eps, blk + o_eps, (size_t)B * n_rec * 8, cudaMemcpyDeviceToHost, st));
+    if (depth) CU(ctx, cudaMemcpyAsync(depth, blk + o_dep, (size_t)B * n_rec * 4, cudaMemcpyDeviceToHost, st));
+    if (n_leapfrog) CU(ctx, cudaMemcpyAsync(n_leapfrog, blk + o_nl, (size_t)B * n_rec * 4, cudaMemcpyDeviceToHost, st));
+    if (divergent) CU(ctx, cudaMemcpyAsync(divergent, blk + o_div, (size_t)B * n_rec * 4, cudaMemcpyDeviceToHost, st));
+    if (status) CU(ctx, cudaMemcpyAsync(status, blk + o_stat, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (n_grad_evals) *n_grad_evals = steps * (long long)B;
+    return GPL_OK;
+}
+
 // ---- sample --------------------------------------------------------------------------------------------------------
 int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,
                double sigma2, double jitter, const double *Z, int S, double *out) {

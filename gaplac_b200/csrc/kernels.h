@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "mcmc_core.h"
 #include "program.h"
 
 namespace gpl {
@@ -88,6 +89,29 @@ __global__ void lk_gradc_kernel(const __grid_constant__ LkGradParams prm);    //
 __global__ void lk_gradsum_kernel(const __grid_constant__ LkGradParams prm);  // grid ceil(B / 128)
 size_t lk_winv_smem_bytes();
 size_t lk_grad_smem_bytes();
+
+// ---- batched on-device sampler (mcmc.cu; per-chain logic in mcmc_core.h) -----------------------------------------------
+struct McmcDevParams {
+    McmcConfig cfg;
+    int B, chain_offset, n_rec;
+    ChainState *state;      // B
+    double *vec;            // B x vec_stride: the vectors of every chain
+    long long vec_stride;
+    const double *q0;       // B x dim initial positions
+    const double *Y;        // observations, chain b at b * y_stride (0: shared)
+    long long y_stride;
+    double *theta_eval;     // B x p: hyperparameters of the next evaluation
+    double *y_eval;         // B x n: latent vectors of the next evaluation (latent model)
+    const double *lml, *dtheta, *dy;  // results of the last evaluation
+    const int *info;
+    double *theta_out, *lp_out, *accept_out, *eps_out, *q_out;
+    int *depth_out, *nleap_out, *div_out;
+    unsigned int *done;     // chains that reached MC_DONE / MC_FAILED
+};
+__global__ void mcmc_init_kernel(const __grid_constant__ McmcDevParams prm);     // one warp per chain
+__global__ void mcmc_advance_kernel(const __grid_constant__ McmcDevParams prm);  // one warp per chain
+__global__ void mcmc_status_kernel(const ChainState *state, int B, int *status);
+size_t mcmc_state_bytes();
 
 // ---- covariance construction (kbuild.cu) ----------------------------------------------------------------------
 struct CovParams {

@@ -50,6 +50,22 @@ struct ChainState {
     double da_mu, da_sbar, da_xbar;
 };
 
+// Stan's windowed-adaptation schedule: 75-step initial buffer, doubling windows from 25, 50-step terminal buffer; shorter
+// warm-ups split 15 % / 75 % / 10 %; below 20 steps the metric is not adapted.
+MC_HD void mc_setup_windows(McmcConfig &c) {
+    c.w_init_buffer = 75;
+    c.w_term_buffer = 50;
+    c.w_base = 25;
+    c.w_enabled = 1;
+    if (c.n_adapt < 20) {
+        c.w_enabled = c.w_init_buffer = c.w_term_buffer = c.w_base = 0;
+    } else if (c.w_init_buffer + c.w_base + c.w_term_buffer > c.n_adapt) {
+        c.w_init_buffer = (int)(0.15 * c.n_adapt);
+        c.w_term_buffer = (int)(0.1 * c.n_adapt);
+        c.w_base = c.n_adapt - (c.w_init_buffer + c.w_term_buffer);
+    }
+}
+
 // vectors of one chain (each `dim` doubles), in this order, followed by r_ck[D] and rs_ck[D]
 enum : int { V_QCUR = 0, V_GCUR, V_QL, V_RL, V_GL, V_QR, V_RR, V_GR, V_RHO, V_QPROP, V_GPROP, V_QSUB, V_GSUB, V_RHOSUB, V_MINV,
              V_WMEAN, V_WM2, V_NFIXED };

@@ -174,6 +174,44 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
                         const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter, int B,
                         int m, const double *Xs, double *mean, double *var, double *lml, int *info);
 
+/* ---- batched on-device sampler: replaces sample(m, NUTS(0.65), N) on the mcmc model body -------------------------------
+ * CLI/src/mcmc.jl:31-41 [upstream Turing 0.21.1 / AdvancedHMC 0.3.5].  The model of every chain b (position in
+ * unconstrained space q = (u, fx)):
+ *     theta_k = lo_k + (hi_k - lo_k) sigmoid(u_k)      hyperparameter slots, Uniform(lo_k, hi_k) priors   (mcmc.jl:32)
+ *     fx ~ N(0, K(X; theta) + (sigma2 + jitter) I)     latent function values                              (mcmc.jl:35)
+ *     Y_b ~ N(fx, obs_sd^2 I)                          observations                                        (mcmc.jl:36)
+ * (latent = 0: Y_b ~ N(0, K + (sigma2 + jitter) I) directly, hyperparameters only.)  B independent chains - one per
+ * column of Y (y_batched: the features of a table) or B chains of the same response - advance in lockstep: one batched
+ * log-density + analytic-gradient evaluation per leapfrog step for all chains, then one state-machine kernel; proposals,
+ * multinomial NUTS trees (generalised U-turn criterion, depth <= max_depth, divergence threshold max_dh), accept/reject
+ * and the warm-up (step-size search, dual averaging to `delta`, Stan's windowed diagonal-metric adaptation) stay on the
+ * device.  Random numbers: Philox4x32-10 keyed by `seed`, counter = (chain_offset + b, transition, index, purpose): a
+ * chain's draws do not depend on B, on the device count or on the execution order (oracle/nuts_ref.py replays them).
+ * Outputs, one record per kept transition (n_rec = n_samples, + n_adapt when record_warmup), chain-major:
+ *   theta (p x n_rec x B), lp (n_rec x B; constrained-space log joint, Turing's `lp` column read by select --chains),
+ *   q (dim x n_rec x B, optional), accept, eps (n_rec x B), depth, n_leapfrog, divergent (n_rec x B ints),
+ *   status (B): 0 ok, 1 the initial point q0 has zero density, 2 not finished.  n_grad_evals: batched evaluations x B. */
+typedef struct gpl_mcmc_opts {
+    int32_t n_samples;     /* N of `--samples` (CLI/src/main.jl:65-71, default 200) */
+    int32_t n_adapt;       /* warm-up transitions; < 0: min(1000, N / 2) as Turing's NUTS(0.65) */
+    int32_t max_depth;     /* <= 10; 0: 10 */
+    int32_t latent;        /* 1: the reference's model */
+    int32_t search_eps;    /* 1: find the initial step size (doubling heuristic) starting from eps0; 0: use eps0 */
+    int32_t adapt_mass;    /* 1: windowed diagonal-metric adaptation */
+    int32_t record_warmup; /* 1: also return the warm-up transitions */
+    int32_t chain_offset;  /* global index of chain 0 (sharding chains over devices keeps every chain's random stream) */
+    double delta;          /* target acceptance (0.65) */
+    double max_dh;         /* divergence threshold (1000) */
+    double obs_sd;         /* 1 */
+    double eps0;           /* 0.1 */
+    uint64_t seed;
+} gpl_mcmc_opts;
+int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, int x_batched, const double *Y,
+                  int y_batched, int p, const double *lo, const double *hi, const double *sigma2, int sigma2_batched,
+                  double jitter, int B, const double *q0, const gpl_mcmc_opts *opts, double *theta, double *lp, double *q,
+                  double *accept, double *eps, int *depth, int *n_leapfrog, int *divergent, int *status,
+                  long long *n_grad_evals);
+
 /* ---- prior sample: replaces rand(gp(X, sigma2)) (CLI/src/sample.jl:25) --------------------------------
  * out (n x S) = U' Z with caller-supplied standard normals Z (n x S): the RNG stays in the host. */
 int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *theta, int p,

@@ -20,6 +20,7 @@ struct TeamSerial {
 typedef void (*grad_fn)(const double *theta, const double *y, double *lml, int *info, double *dth, double *dy);
 
 extern "C" int mc_host_config_size() { return (int)sizeof(McmcConfig); }
+extern "C" void mc_host_setup_windows(McmcConfig *c) { mc_setup_windows(*c); }
 
 extern "C" int mc_host_run(const McmcConfig *cfg, int chain, const double *Y, const double *q0, grad_fn grad, double *theta_out,
                            double *lp, double *accept, double *eps, int *depth, int *n_leap, int *divergent, double *q_out,
