@@ -1,6 +1,6 @@
 // Per-chain state machine of the batched on-device sampler (NUTS with Stan-style warm-up), written once for host and
 // device: the CUDA driver (mcmc.cu) runs it with one warp per chain, tests/test_mcmc_core.py compiles the same header for
-// the host and checks it transition by transition against the NumPy reference sampler (oracle/nuts_ref.py).
+// the host and checks it transition by transition against the independent NumPy reference sampler of the test suite.
 //
 // Replaces `sample(m, NUTS(0.65), N)` on the model body of CLI/src/mcmc.jl:31-41 [upstream Turing 0.21.1 /
 // AdvancedHMC 0.3.5]: multinomial NUTS, generalised U-turn criterion, max depth 10, divergence threshold 1000, diagonal
