@@ -5,6 +5,8 @@ the stream the library runs on and checked against the CPU oracle on a sample (o
     C3             2000 features x n=300, Cat*SqExp+Noise: lml, lml+gradient
     golden         the reference's legacy fixture model, n=923, 200 chain rows (answers = the fixture's own values)
     C1             README workflow: one log-density + gradient call of the mcmc model body, n=50 (host-buffer ABI latency)
+    C1 mcmc        the README command itself: gaplac mcmc "y ~| SqExp(:x)" --samples 500 on the device sampler (1 chain, and 64)
+    C3 mcmc        one chain per feature: 2000 chains x n=300 in lockstep (50 draws after 25 warm-up: bounded sample)
     C4             posterior fit n=2048 + mean/variance at 20 000 test points
     C5             single large GP n=8192: covariance build + blocked Cholesky + solve (gpl_lml_large)
 
@@ -96,6 +98,41 @@ def run_configs(ctx, dev, flush, quick: bool = False):
                       "oracle_max_rel_err": float(abs(res[0][0] - ref) / abs(ref)),
                       "oracle_grad_max_rel_err": float(max(abs(res[2][0, 0] - rdth[0]) / max(1.0, abs(rdth[0])),
                                                            np.max(np.abs(res[3][0] - rdy))))}
+
+    # ---- C1 / C3 through the on-device sampler (gpl_mcmc_nuts) ------------------------------------------------------------------
+    from gaplac_b200 import mcmc
+    from oracle import nuts_ref as NR
+
+    def sampler_entry(label, res, n_chains, n, note):
+        T = res["n_adapt"] + res["n_samples"]
+        return {"workload": label, "chains": n_chains, "n": n, "n_samples": res["n_samples"], "n_adapt": res["n_adapt"],
+                "seconds": res["seconds"], "samples_per_s": n_chains * res["n_samples"] / res["seconds"],
+                "transitions_per_s": n_chains * T / res["seconds"], "grad_evals": int(res["grad_evals"]),
+                "grad_evals_per_s": res["grad_evals"] / res["seconds"], "mean_accept": float(res["accept"].mean()),
+                "mean_tree_depth": float(res["depth"].mean()), "divergent_frac": float(res["divergent"].mean()),
+                "failed_chains": int((res["status"] != 0).sum()), "timing": "wall clock of the blocking call (H2D, graph replay of "
+                "(batched lml+gradient, chain state machine) per leapfrog step, D2H of the chains)", "note": note}
+
+    d = W.make_c1()
+    prog = ctx.program(d["ops"])
+    mcmc.nuts(ctx, prog, d["X"], d["y"], [0.0], [20.0], sigma2=0.1, n_samples=20, n_adapt=10, seed=1)      # warm the graph path
+    r1 = mcmc.nuts(ctx, prog, d["X"], d["y"], [0.0], [20.0], sigma2=0.1, n_samples=500, seed=1, chains=1)
+    e = sampler_entry("C1 gaplac mcmc \"y ~| SqExp(:x)\" n=50, 500 samples (+250 warm-up), 1 chain", r1, 1, 50,
+                      "the reference's own configuration: one chain; latency-bound (7 small launches per leapfrog step)")
+    # fixed-seed parity: the first transitions of the same chain on the host reference sampler
+    rw = mcmc.nuts(ctx, prog, d["X"], d["y"], [0.0], [20.0], sigma2=0.1, n_samples=4, n_adapt=8, seed=1, chains=1,
+                   record_warmup=True, record_q=True)
+    model = NR.Model(d["ops"], d["X"], d["y"], np.array([0.0]), np.array([20.0]), 0.1)
+    ref = NR.sample_chain(model, np.zeros(model.dim), 4, 8, seed=1, chain=0)
+    e["reference_sampler_max_rel_err_first_6_transitions"] = float(max(
+        np.max(np.abs(rw[k][0][:6] - ref[k][:6]) / np.maximum(1.0, np.abs(ref[k][:6]))) for k in ("q", "theta", "lp", "eps", "accept")))
+    e["reference_sampler_same_trees_first_12"] = bool(np.array_equal(rw["depth"][0][:12], ref["depth"][:12]))
+    out["c1_mcmc"] = e
+    r64 = mcmc.nuts(ctx, prog, d["X"], d["y"], [0.0], [20.0], sigma2=0.1, n_samples=500, seed=1, chains=64)
+    out["c1_mcmc_64_chains"] = sampler_entry("C1 model, 64 chains x 500 samples in lockstep", r64, 64, 50, "same launches, 64 chains")
+    r3 = mcmc.nuts(ctx, ctx.program(c3["ops"]), c3["X"], c3["Y"], [0.0, 0.0], [100.0, 2.0], sigma2=0.0, n_samples=50, n_adapt=25, seed=3)
+    out["c3_mcmc"] = sampler_entry("C3 2000 feature chains x n=300, Cat*SqExp+Noise, l ~ U(0,100), s2 ~ U(0,2): 50 draws + 25 warm-up each",
+                                   r3, len(c3["Y"]), 300, "bounded sample of the config's chains (the full run is the same loop, longer)")
 
     # ---- C4: posterior fit n=2048 + 20 000 test points (host-buffer ABI on torch's stream: CUDA events see it) -------------
     d = W.make_c4()

@@ -8,7 +8,8 @@ This package is the host-side mirror of the reference's interface for that path:
 from .formula import (Cat, Constant, GPComponent, GPOperation, Gaussian, KernelProgram, Linear, Noise, Op, OU, Slot,
                       Spec, SqExp, formula, gp_spec, kernel, likelihood, make_gp, parse_formula, response, varnames)
 from .gp import GP, FiniteGP, PosteriorGP, default_context, logpdf, logpdf_batched, mean, mean_and_var, posterior, rand
-from ._lib import Context, GaplacError, PosDefException, Program
+from ._lib import Context, GaplacError, MultiContext, PosDefException, Program
+from . import mcmc
 from .chain import (log2_harmmean_exp2, log_bayes_factor, log_evidence_harmonic, mixture_summary, predict_chain,
                     select_chains_log2_bayes, select_formulae_log2_bayes)
 
@@ -16,7 +17,7 @@ __all__ = [
     "Cat", "Constant", "GPComponent", "GPOperation", "Gaussian", "KernelProgram", "Linear", "Noise", "Op", "OU",
     "Slot", "Spec", "SqExp", "formula", "gp_spec", "kernel", "likelihood", "make_gp", "parse_formula", "response",
     "varnames", "GP", "FiniteGP", "PosteriorGP", "default_context", "logpdf", "logpdf_batched", "mean",
-    "mean_and_var", "posterior", "rand", "Context", "GaplacError", "PosDefException", "Program",
+    "mean_and_var", "posterior", "rand", "Context", "GaplacError", "MultiContext", "PosDefException", "Program", "mcmc",
     "predict_chain", "mixture_summary", "log_evidence_harmonic", "log_bayes_factor", "log2_harmmean_exp2",
     "select_chains_log2_bayes", "select_formulae_log2_bayes",
 ]

@@ -24,7 +24,8 @@ SYMBOLS = [
     "gpl_cov", "gpl_cov_dev", "gpl_cross_cov", "gpl_lml_batched", "gpl_lml_batched_dev", "gpl_posterior_fit",
     "gpl_posterior_free", "gpl_posterior_logpdf", "gpl_posterior_alpha", "gpl_posterior_factor",
     "gpl_posterior_mean_var", "gpl_sample", "gpl_chol_logdet", "gpl_chol_logdet_dev", "gpl_lml_large",
-    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream", "gpl_mcmc_nuts",
+    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream", "gpl_mcmc_nuts", "gpl_multi_init", "gpl_multi_destroy",
+    "gpl_multi_device_count", "gpl_multi_context", "gpl_multi_last_error", "gpl_multi_lml_batched", "gpl_multi_mcmc_nuts",
 ]
 
 
@@ -81,6 +82,16 @@ def load() -> C.CDLL:
     lib.gpl_device_info.argtypes = [_vp, C.c_char_p, C.c_int, _ip, _ip]
     lib.gpl_last_timing.argtypes = [_vp, C.POINTER(GplTiming)]
     lib.gpl_set_stream.argtypes = [_vp, _vp]
+    lib.gpl_multi_init.argtypes = [_ip, C.c_int, C.POINTER(_vp)]
+    lib.gpl_multi_destroy.argtypes = [_vp]
+    lib.gpl_multi_device_count.argtypes = [_vp]
+    lib.gpl_multi_context.argtypes = [_vp, C.c_int]
+    lib.gpl_multi_context.restype = _vp
+    lib.gpl_multi_last_error.argtypes = [_vp]
+    lib.gpl_multi_last_error.restype = C.c_char_p
+    lib.gpl_multi_mcmc_nuts.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
+                                        C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        C.POINTER(C.c_longlong)]
     lib.gpl_mcmc_nuts.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
                                   C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.POINTER(C.c_longlong)]
@@ -94,6 +105,7 @@ def load() -> C.CDLL:
     lml_args = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_double,
                 C.c_int, _vp, _vp, _vp, _vp]
     lib.gpl_lml_batched.argtypes = lml_args
+    lib.gpl_multi_lml_batched.argtypes = lml_args
     lib.gpl_lml_batched_dev.argtypes = lml_args + [_vp]
     lib.gpl_posterior_fit.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, C.c_double,
                                       C.POINTER(_vp)]
@@ -211,8 +223,86 @@ class Posterior:
             pass
 
 
+def _lml_batched_call(fn, owner, prog, X, Y, Theta, sigma2, jitter, grad):
+    """Argument marshalling shared by Context.lml_batched and MultiContext.lml_batched (same C signature)."""
+    Theta = np.ascontiguousarray(np.atleast_2d(np.asarray(Theta, dtype=np.float64)))  # (B,p) C-order == p x B col-major
+    B, p = Theta.shape
+    Xa = np.asarray(X, dtype=np.float64)
+    x_batched = Xa.ndim == 3
+    if x_batched:
+        n, d = Xa.shape[1], Xa.shape[2]
+        Xf = np.ascontiguousarray(np.transpose(Xa, (0, 2, 1)))  # per item: column-major n x d
+    else:
+        Xf = _fa(Xa, 2)
+        n, d = Xf.shape
+    Ya = np.asarray(Y, dtype=np.float64)
+    y_batched = Ya.ndim == 2
+    Yc = np.ascontiguousarray(Ya)  # (B, n) C-order == n x B col-major
+    s2 = np.ascontiguousarray(np.atleast_1d(np.asarray(sigma2, dtype=np.float64)))
+    s_batched = s2.size > 1
+    lml = np.empty(B)
+    info = np.zeros(B, dtype=np.int32)
+    dth = np.empty((B, p)) if grad else None
+    dy = np.empty((B, n)) if grad else None
+    owner._check(fn(owner.h, prog.h, n, d, _ptr(Xf), int(x_batched), _ptr(Yc), int(y_batched), _ptr(Theta), p, _ptr(s2),
+                    int(s_batched), jitter, B, _ptr(lml), _ptr(dth) if grad else None, _ptr(dy) if grad else None,
+                    info.ctypes.data_as(_vp)))
+    return (lml, info, dth, dy) if grad else (lml, info)
+
+
+class _NoCtx:
+    h = None
+
+
+class MultiContext:
+    """gpl_multi: one context per device behind one handle; batched calls shard their independent items over the devices
+    and gather into the caller's buffers (one call, as a Julia host would make one `ccall`)."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+        h = _vp()
+        rc = load().gpl_multi_init(devs, len(devices), C.byref(h))
+        if rc != GPL_OK:
+            msg = load().gpl_multi_last_error(None)
+            raise GaplacError(rc, msg.decode() if msg else "")
+        self.h = h
+        self.devices = list(devices)
+
+    def _check(self, rc: int) -> None:
+        if rc != GPL_OK:
+            msg = load().gpl_multi_last_error(self.h)
+            raise GaplacError(rc, msg.decode() if msg else "")
+
+    def program(self, ops) -> Program:
+        return Program(_NoCtx, ops)      # programs are device-independent
+
+    def set_option(self, key: str, value: int) -> None:
+        for r in range(len(self.devices)):
+            _check(None, load().gpl_set_option(load().gpl_multi_context(self.h, r), key.encode(), value))
+
+    def launch_count(self) -> int:
+        return sum(int(load().gpl_launch_count(load().gpl_multi_context(self.h, r))) for r in range(len(self.devices)))
+
+    def lml_batched(self, prog: Program, X, Y, Theta, sigma2, jitter: float = 0.0, grad: bool = False):
+        return _lml_batched_call(load().gpl_multi_lml_batched, self, prog, X, Y, Theta, sigma2, jitter, grad)
+
+    def close(self):
+        if self.h:
+            load().gpl_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """gpl_ctx: one CUDA device, one stream, a grow-only workspace pool."""
+
+    def _check(self, rc: int) -> None:
+        _check(self.h, rc)
 
     def __init__(self, device: int = -1):
         h = _vp()
@@ -268,6 +358,11 @@ class Context:
         _check(self.h, load().gpl_cov(self.h, prog.h, n, d, _ptr(X), _ptr(th), th.size, sigma2, jitter, _ptr(K)))
         return K
 
+    def cov_dev(self, prog: Program, n: int, d: int, dX: int, dtheta: int, p: int, sigma2: float, jitter: float, dK: int,
+                stream: int = 0) -> None:
+        """Device-pointer entry: K (n x n, column-major) into dK; asynchronous on `stream`."""
+        _check(self.h, load().gpl_cov_dev(self.h, prog.h, n, d, dX, dtheta or None, p, sigma2, jitter, dK, stream or None))
+
     def cross_cov(self, prog: Program, X, Xs, theta) -> np.ndarray:
         X, Xs = _fa(X, 2), _fa(Xs, 2)
         n, d = X.shape
@@ -281,30 +376,7 @@ class Context:
     def lml_batched(self, prog: Program, X, Y, Theta, sigma2, jitter: float = 0.0, grad: bool = False):
         """X: (n, d) shared or (B, n, d); Y: (n,) shared or (B, n); Theta: (B, p); sigma2: scalar or (B,).
         Returns (lml[B], info[B]) or, with grad, (lml, info, dtheta[B, p], dy[B, n])."""
-        Theta = np.ascontiguousarray(np.atleast_2d(np.asarray(Theta, dtype=np.float64)))  # (B,p) C-order == p x B col-major
-        B, p = Theta.shape
-        Xa = np.asarray(X, dtype=np.float64)
-        x_batched = Xa.ndim == 3
-        if x_batched:
-            n, d = Xa.shape[1], Xa.shape[2]
-            Xf = np.ascontiguousarray(np.transpose(Xa, (0, 2, 1)))  # per item: column-major n x d
-        else:
-            Xf = _fa(Xa, 2)
-            n, d = Xf.shape
-        Ya = np.asarray(Y, dtype=np.float64)
-        y_batched = Ya.ndim == 2
-        Yc = np.ascontiguousarray(Ya)  # (B, n) C-order == n x B col-major
-        s2 = np.ascontiguousarray(np.atleast_1d(np.asarray(sigma2, dtype=np.float64)))
-        s_batched = s2.size > 1
-        lml = np.empty(B)
-        info = np.zeros(B, dtype=np.int32)
-        dth = np.empty((B, p)) if grad else None
-        dy = np.empty((B, n)) if grad else None
-        _check(self.h, load().gpl_lml_batched(
-            self.h, prog.h, n, d, _ptr(Xf), int(x_batched), _ptr(Yc), int(y_batched), _ptr(Theta), p, _ptr(s2),
-            int(s_batched), jitter, B, _ptr(lml), _ptr(dth) if grad else None, _ptr(dy) if grad else None,
-            info.ctypes.data_as(_vp)))
-        return (lml, info, dth, dy) if grad else (lml, info)
+        return _lml_batched_call(load().gpl_lml_batched, self, prog, X, Y, Theta, sigma2, jitter, grad)
 
     def lml_batched_dev(self, prog: Program, n: int, d: int, dX: int, x_batched: bool, dY: int, y_batched: bool,
                         dTheta: int, p: int, dsigma2: int, sigma2_batched: bool, jitter: float, B: int, dlml: int,

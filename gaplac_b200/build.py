@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libgaplac_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-format-truncation"]
 CU_SOURCES = ["api.cu", "lml_batched.cu", "lml_lockstep.cu", "lml_grad_lockstep.cu", "mcmc.cu", "kbuild.cu", "big.cu", "predict.cu"]
-CPP_SOURCES = ["program.cpp"]
+CPP_SOURCES = ["program.cpp", "multi.cpp"]
 
 
 def _newest_header() -> float:
@@ -62,7 +62,7 @@ def build_variant(tag: str, defs: list[str]) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdr_time = _newest_header()
-    with ThreadPoolExecutor(max_workers=8) as ex:
+    with ThreadPoolExecutor(max_workers=10) as ex:
         res = list(ex.map(lambda s: _compile(s, force, hdr_time), CU_SOURCES + CPP_SOURCES))
     objs = [r[0] for r in res]
     if force or any(r[1] for r in res) or not os.path.exists(LIB):

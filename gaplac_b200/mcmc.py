@@ -99,11 +99,12 @@ def nuts(ctx, prog, X, Y, lo, hi, sigma2=0.1, n_samples=200, n_adapt=None, seed=
     evals = C.c_longlong(0)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     t0 = time.perf_counter()
-    rc = lib.gpl_mcmc_nuts(ctx.h, prog.h, n, d, vp(Xf), int(x_batched), vp(Y), int(y_batched), p, vp(lo), vp(hi), vp(s2),
+    fn = lib.gpl_multi_mcmc_nuts if isinstance(ctx, _lib.MultiContext) else lib.gpl_mcmc_nuts   # same signature
+    rc = fn(ctx.h, prog.h, n, d, vp(Xf), int(x_batched), vp(Y), int(y_batched), p, vp(lo), vp(hi), vp(s2),
                            int(s2.size > 1), C.c_double(jitter), B, vp(q0a), C.byref(opts), vp(out["theta"]), vp(out["lp"]),
                            vp(out["q"]) if record_q else None, vp(out["accept"]), vp(out["eps"]), vp(out["depth"]),
                            vp(out["n_leapfrog"]), vp(out["divergent"]), vp(out["status"]), C.byref(evals))
-    _lib._check(ctx.h, rc)
+    ctx._check(rc)
     out["seconds"] = time.perf_counter() - t0
     out["grad_evals"] = evals.value
     out["n_adapt"], out["n_samples"] = n_adapt, n_samples

@@ -227,6 +227,30 @@ int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double
 int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X, const double *y,
                   const double *theta, int p, double sigma2, double jitter, double *lml, double *logdet, int *info);
 
+/* ---- several GPUs behind one call (SURVEY.md 8(b) "device(s)", 8(e) "one ccall") ------------------------------------------
+ * A gpl_multi owns one context per listed device (devices = NULL: ordinals 0 .. n_devices-1; a device may be listed
+ * twice).  The batched calls split the B independent items into contiguous blocks - the first B mod R blocks one item
+ * longer, the rule of gaplac_b200/shard.py - run every block concurrently on its device and let each device write its
+ * slice of the outputs straight into the caller's host buffers: the gather IS the device-to-host copy, there is no
+ * collective on the data path.  Semantics, layouts and per-item error reporting are those of gpl_lml_batched /
+ * gpl_mcmc_nuts; results do not depend on the number of devices (chains keep their random streams: chain_offset).
+ * A gpl_prog is device-independent and can be shared (gpl_program_create accepts ctx = NULL).  The reference has no
+ * counterpart: one Julia task evaluates one model at a time (CLI/src/mcmc.jl:41, CLI/src/select.jl:49-50). */
+typedef struct gpl_multi gpl_multi;
+int gpl_multi_init(const int *devices, int n_devices, gpl_multi **out);
+int gpl_multi_destroy(gpl_multi *m);
+int gpl_multi_device_count(const gpl_multi *m);
+gpl_ctx *gpl_multi_context(gpl_multi *m, int part); /* the context of part r (options, timing); owned by m */
+const char *gpl_multi_last_error(gpl_multi *m);
+int gpl_multi_lml_batched(gpl_multi *m, const gpl_prog *prog, int n, int d, const double *X, int x_batched, const double *Y,
+                          int y_batched, const double *Theta, int p, const double *sigma2, int sigma2_batched, double jitter,
+                          int B, double *lml, double *dtheta, double *dy, int *info);
+int gpl_multi_mcmc_nuts(gpl_multi *m, const gpl_prog *prog, int n, int d, const double *X, int x_batched, const double *Y,
+                        int y_batched, int p, const double *lo, const double *hi, const double *sigma2, int sigma2_batched,
+                        double jitter, int B, const double *q0, const gpl_mcmc_opts *opts, double *theta, double *lp, double *q,
+                        double *accept, double *eps, int *depth, int *n_leapfrog, int *divergent, int *status,
+                        long long *n_grad_evals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,3 +81,14 @@ def test_fast_exp_vec_group_matches_scalar_including_a_slow_path_member(lib):
         ok = ~np.isnan(ref)
         assert np.array_equal(np.isnan(out), np.isnan(ref))
         assert np.allclose(out[ok], ref[ok], rtol=4e-16, atol=0.0)
+
+
+def test_fast_exp_vec_deep_underflow_group_is_flushed_branch_free(lib):
+    """A group with arguments below -700 but no NaN / overflow takes the clamped branch-free path: exact zeros below
+    -708 (the true values are below 3.3e-308), the usual <= 1.5 ulp elsewhere - also between -700 and -708."""
+    x = np.array([-0.25, -699.0, -703.5, -707.9, -708.5, -745.0, -5000.0, -np.inf])
+    out = np.empty(8)
+    lib.fast_exp_vec8(np.ascontiguousarray(x).ctypes.data, out.ctypes.data)
+    ref = np.exp(x)
+    assert np.all(out[4:] == 0.0) and np.all(ref[4:] < 3.4e-308)
+    assert np.allclose(out[:4], ref[:4], rtol=4e-16, atol=0.0)
