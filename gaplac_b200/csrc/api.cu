@@ -450,7 +450,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
-    const size_t nflags = (size_t)BIG_MAXP + 3 * (size_t)nt;
+    const size_t nflags = (size_t)BIG_MAXP + 3 * (size_t)nt + 1;  // ... + the abort flag of the bounded waits
     int rc = ensure(ctx, ctx->bigFlags, nflags * sizeof(int));
     if (rc) return rc;
     prm.flags = ptr<int>(ctx->bigFlags);
@@ -976,6 +976,7 @@ static int posterior_fit_impl(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, 
         CU(ctx, cudaStreamSynchronize(st));
         h_lml = -0.5 * ((double)n * LOG2PI + h_res[0] + h_res[1]);
     }
+    if (h_info < 0) return fail(ctx, GPL_ERR_CUDA, "large-n factorisation: a hand-off between its kernels timed out (device busy?)");
     if (h_info != 0)
         return fail(ctx, GPL_ERR_NOTPD, "covariance not positive definite: pivot %d (PosDefException(%d))", h_info, h_info);
     post->lml = h_lml;
@@ -1494,6 +1495,7 @@ int gpl_chol_logdet(gpl_ctx *ctx, int n, double *A, int want_factor, double *log
     CU(ctx, cudaStreamSynchronize(st));
     if (info) *info = h_info;
     if (h_info) *logdet = NAN;
+    if (h_info < 0) return fail(ctx, GPL_ERR_CUDA, "large-n factorisation: a hand-off between its kernels timed out (device busy?)");
     return GPL_OK;
 }
 
@@ -1556,6 +1558,7 @@ int gpl_lml_large(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
         ctx->lk_ms[2] = 0.0;
         for (auto &e : ev) cudaEventDestroy(e);
     }
+    if (h_info < 0) return fail(ctx, GPL_ERR_CUDA, "large-n factorisation: a hand-off between its kernels timed out (device busy?)");
     if (info) *info = h_info;
     if (logdet) *logdet = h_info ? NAN : h_res[0];
     *lml = h_info ? -INFINITY : -0.5 * ((double)n * LOG2PI + h_res[0] + h_res[1]);

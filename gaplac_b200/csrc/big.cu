@@ -175,12 +175,30 @@ __global__ void __launch_bounds__(NTHREADS) big_col_kernel(BigParams prm) {
 //   tiledone[i]     = j + 1 once tile (i, j) is final                            (written by big_col_flag_kernel)
 //   rowdone[i]      = j + 1 once, in addition, y_i carries column j              (written by big_col_flag_kernel)
 //   diagdone[j]     1 once L_jj and its block inverses are stored, 2 once z_j is   (written by the worker)
+//   abort           set by whoever waits longer than BIG_WAIT_NS for a hand-off: every later wait returns at once, the
+//                   factorisation finishes with garbage and info = -1, and the host reports GPL_ERR_CUDA.  Forward progress
+//                   of the protocol needs the worker CTA and at least one column CTA resident at the same time; a bounded wait
+//                   turns a lost hand-off (or a device shared with something that keeps them apart) into an error, not a hang.
+constexpr unsigned long long BIG_WAIT_NS = 2000000000ull;  // 2 s; hand-offs normally take microseconds
 __device__ __forceinline__ int ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
-__device__ __forceinline__ void wait_flag_ge(const int *p, int v, int tid) {
-    if (tid == 0) {
-        while (ld_flag(p) < v) __nanosleep(40);
-        __threadfence();
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_flag_ge(const int *p, int v, int tid, int *abort_flag, int *info) {
+    if (tid == 0 && ld_flag(p) < v) {
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_flag(p) < v && ld_flag(abort_flag) == 0) {
+            __nanosleep(40);
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > BIG_WAIT_NS) {
+                atomicExch(abort_flag, 1);
+                atomicExch(info, -1);
+            }
+        }
     }
+    if (tid == 0) __threadfence();
     __syncthreads();
 }
 
@@ -190,6 +208,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
     const int tid = threadIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
     int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
+    int *abort_flag = tiledone + nt;
     constexpr int PANEL_ = BIG_PANEL;
 #ifdef GPL_BIG_PROFILE
     long long t_wait_panel = 0, t_wait_row = 0, t_begin = clock64(), t_pre = 0, t_last = 0, t_potrf = 0, t_pub = 0, t_fwd = 0;
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
 #ifdef GPL_BIG_PROFILE
         long long ta = clock64();
 #endif
-        if (j == k0) wait_flag_ge(panel_ready + j / PANEL_, 1, tid);
+        if (j == k0) wait_flag_ge(panel_ready + j / PANEL_, 1, tid, abort_flag, prm.info);
 #ifdef GPL_BIG_PROFILE
         long long tb = clock64();
         t_wait_panel += tb - ta;
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         // on the serial path.
         double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
         double acc[2][NCC];
-        if (j - k0 >= 2) wait_flag_ge(tiledone + j, j - 1, tid);  // tiles (j, k0..j-2) are final (normally long since)
+        if (j - k0 >= 2) wait_flag_ge(tiledone + j, j - 1, tid, abort_flag, prm.info);  // tiles (j, k0..j-2) are final (normally long since)
         __syncthreads();
         tile_load_async(sm.A, Tjj, tid);
         cp_async_commit();
@@ -238,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         long long tc = clock64();
         t_pre += tc - tb;
 #endif
-        if (j > 0) wait_flag_ge(tiledone + j, j, tid);
+        if (j > 0) wait_flag_ge(tiledone + j, j, tid, abort_flag, prm.info);
 #ifdef GPL_BIG_PROFILE
         long long td = clock64();
         t_wait_row += td - tc;
@@ -278,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker_kernel(BigParams prm) {
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
         if (prm.y) {  // z_j while the column CTAs load L_jj and solve: they need it only for their right-hand sides
             acc_to_tile(sm.A, acc, tm);
-            if (j > 0) wait_flag_ge(rowdone + j, j, tid);  // y_j carries every earlier column (set after tiledone)
+            if (j > 0) wait_flag_ge(rowdone + j, j, tid, abort_flag, prm.info);  // y_j carries every earlier column (set after tiledone)
             if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
             tile_forward_solve(sm.A, sm.D, sm.ybuf, sm.rsbuf, tid);  // z_j = L_jj^-1 y_j
             if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
     ColSmem &sm = *reinterpret_cast<ColSmem *>(smem_raw);
     const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
-    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
+    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt, *abort_flag = tiledone + nt;
     double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
     // the tile itself receives no further outside update: fetch it while the worker is still on the diagonal tile
     tile_load_async(sm.A, Tij, tid);
@@ -324,7 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
         __syncthreads();
         tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
     }
-    wait_flag_ge(diagdone + j, 1, tid);  // L_jj and its block inverses are stored
+    wait_flag_ge(diagdone + j, 1, tid, abort_flag, prm.info);  // L_jj and its block inverses are stored
     __syncthreads();  // the last update's operands are consumed: Bt takes L_jj
     tile_load_async(sm.Bt, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
     block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
@@ -338,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
     if (tid == 0) *reinterpret_cast<volatile int *>(tiledone + i) = j + 1;  // the worker's next update needs only the tile
     if (prm.y) {
         acc_to_tile(sm.A, acc, tm);
-        wait_flag_ge(diagdone + j, 2, tid);  // z_j (published after L_jj; normally long since)
+        wait_flag_ge(diagdone + j, 2, tid, abort_flag, prm.info);  // z_j (published after L_jj; normally long since)
         if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
         __syncthreads();
         if (tid < TS) prm.y[i * TS + tid] = __ldcg(prm.y + i * TS + tid) - tile_row_dot(sm.A, sm.ybuf, tid, 0, TS);

@@ -219,7 +219,9 @@ int gpl_sample(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double *X
 
 /* ---- single large-n factorisation (BASELINE config 5): cholesky(Symmetric(A)) + logdet -----------------
  * A (n x n, column-major, symmetric; only the lower triangle is read) is overwritten by the upper factor U
- * when `want_factor` != 0; logdet = 2 sum log U_ii.  *info = 0 or the failing pivot. */
+ * when `want_factor` != 0; logdet = 2 sum log U_ii.  *info = 0 or the failing pivot; -1 (with GPL_ERR_CUDA from the host
+ * entry points) if a hand-off between the concurrently running kernels of the factorisation timed out (bounded waits:
+ * a device kept busy by other work yields an error, never a hang). */
 int gpl_chol_logdet(gpl_ctx *ctx, int n, double *A, int want_factor, double *logdet, int *info);
 int gpl_chol_logdet_dev(gpl_ctx *ctx, int n, double *dA, int want_factor, double *dlogdet, int *dinfo, void *stream);
 /* fused: build K_y from the program on the device, factor it, return logdet and lml without K ever
