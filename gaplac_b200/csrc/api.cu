@@ -54,6 +54,7 @@ struct gpl_ctx {
     int chol_variant = 0;
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
     size_t lk_ws_limit = (size_t)24 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
+    int poison_ws = 0;                      // 1: fill the whole workspace with NaN payloads before every call (hygiene tests)
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
     int lk_launches[7] = {0, 0, 0, 0, 0, 0, 0};  // alpha / contraction kernels
@@ -101,11 +102,22 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
 // The context owns ONE grow-only workspace.  Calls may arrive on different streams (the *_dev entry points take the
 // caller's stream): every call that touches the workspace first makes its stream wait for the previous such call and
 // records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
+inline void all_buffers(gpl_ctx *ctx, std::vector<DevBuf *> &out) {
+    out = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
+           &ctx->lkM, &ctx->lkGpart, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
+           &ctx->bLml, &ctx->bDtheta, &ctx->bDy, &ctx->bInfo, &ctx->bMisc, &ctx->bK, &ctx->bXs, &ctx->bMean, &ctx->bVar, &ctx->bWsV};
+}
 struct WsOrder {
     gpl_ctx *c;
     cudaStream_t st;
     WsOrder(gpl_ctx *ctx, cudaStream_t s) : c(ctx), st(s) {
         if (c->wsEventSet) cudaStreamWaitEvent(st, c->wsEvent, 0);
+        if (c->poison_ws) {  // every byte 0xFF = NaN payloads: a kernel that reads workspace it did not write shows up in the results
+            std::vector<DevBuf *> bufs;
+            all_buffers(c, bufs);
+            for (DevBuf *b : bufs)
+                if (b->p) cudaMemsetAsync(b->p, 0xFF, b->cap, st);
+        }
     }
     ~WsOrder() {
         if (c->wsEvent && cudaEventRecord(c->wsEvent, st) == cudaSuccess) c->wsEventSet = true;
@@ -612,9 +624,8 @@ int gpl_destroy(gpl_ctx *ctx) {
     }
     ctx->livePosts.clear();
     if (ctx->wsEvent) cudaEventDestroy(ctx->wsEvent);
-    DevBuf *bufs[] = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc, &ctx->lkM, &ctx->lkGpart, &ctx->ws,   &ctx->vec,     &ctx->counter, &ctx->bX,   &ctx->bY,    &ctx->bTheta,
-                      &ctx->bSigma, &ctx->bLml,  &ctx->bDtheta, &ctx->bDy,  &ctx->bInfo, &ctx->bMisc,
-                      &ctx->bK,   &ctx->bXs,     &ctx->bMean,   &ctx->bVar, &ctx->bWsV};
+    std::vector<DevBuf *> bufs;
+    all_buffers(ctx, bufs);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &blk : ctx->postFree) cudaFree(blk.first);
@@ -644,6 +655,7 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "chol_variant")) ctx->chol_variant = value;
     else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
     else if (!strcmp(key, "profile_events")) ctx->profile_events = value;
+    else if (!strcmp(key, "poison_ws")) ctx->poison_ws = value;
     else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
     return GPL_OK;
 }
@@ -1294,7 +1306,10 @@ int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
                  o_lml = take((size_t)B * 8), o_dth = take((size_t)B * pp * 8), o_dy = take((size_t)B * n * 8), o_info = take((size_t)B * 4),
                  o_th = take((size_t)B * n_rec * pp * 8), o_lp = take((size_t)B * n_rec * 8), o_acc = take((size_t)B * n_rec * 8),
                  o_eps = take((size_t)B * n_rec * 8), o_qo = take(q ? (size_t)B * n_rec * dim * 8 : 8), o_dep = take((size_t)B * n_rec * 4),
-                 o_nl = take((size_t)B * n_rec * 4), o_div = take((size_t)B * n_rec * 4), o_done = take(256), o_stat = take((size_t)B * 4);
+                 o_nl = take((size_t)B * n_rec * 4), o_div = take((size_t)B * n_rec * 4), o_done = take(256), o_stat = take((size_t)B * 4),
+                 o_slot = take((size_t)B * 4),
+                 // slot-ordered copies of the per-chain inputs of the evaluation (used after a compaction)
+                 o_xs = take(x_batched ? xb : 8), o_ys = take((y_batched && !opts->latent) ? yb : 8), o_s2s = take(sigma2_batched ? sb : 8);
     char *blk = nullptr;
     CU(ctx, cudaMalloc((void **)&blk, off));
     struct Guard {  // frees the block (and the graph objects) on every exit path
@@ -1338,40 +1353,52 @@ int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     mp.nleap_out = iptr(o_nl);
     mp.div_out = iptr(o_div);
     mp.done = reinterpret_cast<unsigned int *>(blk + o_done);
-    const int warps_per_block = 4, grid = (B + warps_per_block - 1) / warps_per_block;
-    mcmc_init_kernel<<<grid, 32 * warps_per_block, 0, st>>>(mp);
+    mp.n_active = reinterpret_cast<int *>(blk + o_done + 64);
+    mp.slot_chain = iptr(o_slot);
+    mp.n_slots = B;
+    const int warps_per_block = 4;
+    auto warp_grid = [&](int items) { return (items + warps_per_block - 1) / warps_per_block; };
+    mcmc_init_kernel<<<warp_grid(B), 32 * warps_per_block, 0, st>>>(mp);
     ctx->launches++;
+    int n_slots = B;
+    const double *xs = dptr(o_x), *ys = dptr(o_y), *s2s = dptr(o_s2);  // evaluation inputs in slot order
     // one step: evaluate log-density + gradient at every chain's emitted point, then advance every chain
     const int saved_profile = ctx->profile_events;
     ctx->profile_events = 0;
     auto step = [&]() -> int {
-        int r = launch_lml_lockstep(ctx, prog->dev, n, d, dptr(o_x), x_batched, c.latent ? dptr(o_ye) : dptr(o_y),
-                                    c.latent ? 1 : y_batched, dptr(o_the), p, dptr(o_s2), sigma2_batched, jitter, B, dptr(o_lml),
-                                    iptr(o_info), st, dptr(o_dth), dptr(o_dy), 1);
+        int r = launch_lml_lockstep(ctx, prog->dev, n, d, xs, x_batched, c.latent ? dptr(o_ye) : ys, c.latent ? 1 : y_batched,
+                                    dptr(o_the), p, s2s, sigma2_batched, jitter, n_slots, dptr(o_lml), iptr(o_info), st,
+                                    dptr(o_dth), dptr(o_dy), 1);
         if (r) return r;
-        mcmc_advance_kernel<<<grid, 32 * warps_per_block, 0, st>>>(mp);
+        mcmc_advance_kernel<<<warp_grid(n_slots), 32 * warps_per_block, 0, st>>>(mp);
         ctx->launches++;
         return GPL_OK;
     };
     const uint64_t launches_before = ctx->launches;
     rc = step();  // the first step also sizes the workspaces (no allocation may happen inside a capture)
-    const uint64_t launches_per_step = ctx->launches - launches_before;
-    long long steps = 1;
+    uint64_t launches_per_step = ctx->launches - launches_before;  // re-counted at every capture (fewer slots, fewer chunks)
+    long long steps = 1, evals = B;  // evaluations actually launched: slots per step (finished chains leave at compactions)
     unsigned int done = 0;
     if (rc == GPL_OK) {
         // capture one step and replay it; the host only polls the done counter every `poll` steps
-        bool graph_ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-        if (graph_ok) {
-            rc = step();
-            ctx->launches -= launches_per_step;  // captured, not launched
-            cudaError_t e = cudaStreamEndCapture(st, &guard.g);
-            graph_ok = rc == GPL_OK && e == cudaSuccess && guard.g &&
-                       cudaGraphInstantiate(&guard.ge, guard.g, 0) == cudaSuccess;
-            if (!graph_ok) {
-                cudaGetLastError();
-                rc = GPL_OK;
+        bool graph_ok = false;
+        auto capture = [&]() {
+            if (guard.ge) cudaGraphExecDestroy(guard.ge);
+            if (guard.g) cudaGraphDestroy(guard.g);
+            guard.ge = nullptr;
+            guard.g = nullptr;
+            graph_ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (graph_ok) {
+                const uint64_t before = ctx->launches;
+                const int r = step();
+                launches_per_step = ctx->launches - before;
+                ctx->launches = before;  // captured, not launched
+                cudaError_t e = cudaStreamEndCapture(st, &guard.g);
+                graph_ok = r == GPL_OK && e == cudaSuccess && guard.g && cudaGraphInstantiate(&guard.ge, guard.g, 0) == cudaSuccess;
+                if (!graph_ok) cudaGetLastError();
             }
-        }
+        };
+        capture();
         const long long max_steps = (long long)T * ((1LL << c.max_depth) + 1) + 64;
         const int poll = 16;
         while (rc == GPL_OK && done < (unsigned)B && steps < max_steps) {
@@ -1383,10 +1410,34 @@ int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
                     rc = step();
                 }
                 ++steps;
+                evals += n_slots;
             }
             if (rc) break;
             CU(ctx, cudaMemcpyAsync(&done, mp.done, sizeof(done), cudaMemcpyDeviceToHost, st));
             CU(ctx, cudaStreamSynchronize(st));
+            // Compaction: chains finish at different times (their trees differ); once a quarter of the slots idle, the
+            // active chains move to the first slots and the evaluation batch shrinks to them.
+            const int active = B - (int)done;
+            if (active > 0 && n_slots >= 32 && active <= n_slots - n_slots / 4) {
+                mcmc_compact_kernel<<<1, 256, 0, st>>>(mp);
+                int na = 0;
+                CU(ctx, cudaMemcpyAsync(&na, mp.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(ctx, cudaStreamSynchronize(st));
+                if (na < 1 || na > n_slots) return fail(ctx, GPL_ERR_CUDA, "gpl_mcmc_nuts: compaction returned %d active chains", na);
+                n_slots = mp.n_slots = na;
+                mcmc_reemit_kernel<<<warp_grid(n_slots), 32 * warps_per_block, 0, st>>>(mp);
+                ctx->launches += 2;
+                auto gather = [&](size_t src_off, size_t dst_off, long long width, const double *&cur) {
+                    mcmc_gather_kernel<<<256, 256, 0, st>>>(dptr(src_off), dptr(dst_off), mp.slot_chain, n_slots, width);
+                    ctx->launches++;
+                    cur = dptr(dst_off);
+                };
+                if (x_batched) gather(o_x, o_xs, (long long)n * d, xs);
+                if (y_batched && !c.latent) gather(o_y, o_ys, n, ys);
+                if (sigma2_batched) gather(o_s2, o_s2s, 1, s2s);
+                CU(ctx, cudaGetLastError());
+                capture();
+            }
         }
     }
     ctx->profile_events = saved_profile;
@@ -1404,7 +1455,7 @@ int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     if (divergent) CU(ctx, cudaMemcpyAsync(divergent, blk + o_div, (size_t)B * n_rec * 4, cudaMemcpyDeviceToHost, st));
     if (status) CU(ctx, cudaMemcpyAsync(status, blk + o_stat, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
-    if (n_grad_evals) *n_grad_evals = steps * (long long)B;
+    if (n_grad_evals) *n_grad_evals = evals;
     return GPL_OK;
 }
 

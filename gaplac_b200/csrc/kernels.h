@@ -107,9 +107,20 @@ struct McmcDevParams {
     double *theta_out, *lp_out, *accept_out, *eps_out, *q_out;
     int *depth_out, *nleap_out, *div_out;
     unsigned int *done;     // chains that reached MC_DONE / MC_FAILED
+    // Evaluation slots: the batched log-density call runs over n_slots items; slot s belongs to chain slot_chain[s].
+    // theta_eval, y_eval, lml, dtheta, dy, info are indexed by SLOT, everything else by chain.  At start slot = chain;
+    // once enough chains have finished the driver compacts the active chains into the first slots (mcmc_compact_kernel)
+    // so that finished chains stop costing evaluations.
+    int *slot_chain;
+    int n_slots;
+    int *n_active;          // device scalar written by mcmc_compact_kernel
 };
 __global__ void mcmc_init_kernel(const __grid_constant__ McmcDevParams prm);     // one warp per chain
-__global__ void mcmc_advance_kernel(const __grid_constant__ McmcDevParams prm);  // one warp per chain
+__global__ void mcmc_advance_kernel(const __grid_constant__ McmcDevParams prm);  // one warp per slot
+__global__ void mcmc_compact_kernel(const __grid_constant__ McmcDevParams prm);  // 1 CTA: slot_chain <- active chains, in order
+__global__ void mcmc_reemit_kernel(const __grid_constant__ McmcDevParams prm);   // one warp per slot: pending point -> its new slot
+// rows of a per-chain input (width doubles each) into slot order: dst[s] = src[slot_chain[s]]
+__global__ void mcmc_gather_kernel(const double *src, double *dst, const int *slot_chain, int n_slots, long long width);
 __global__ void mcmc_status_kernel(const ChainState *state, int B, int *status);
 size_t mcmc_state_bytes();
 

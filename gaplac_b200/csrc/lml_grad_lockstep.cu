@@ -185,24 +185,36 @@ __global__ void __launch_bounds__(NTHREADS, 3) lk_gradc_kernel(const __grid_cons
     acc_zero(acc);
 #pragma unroll
     for (int s0 = 0; s0 < GNS - 1; ++s0) issue(s0);
+    // Ragged n: the last tile row of M ends in identity padding; in every (M_ki)' with k = nt - 1 the columns kk >= vlast
+    // are zero (or the padding identity, which only reaches entries outside the matrix): those stages are skipped.
+    const int vlast = n - (nt - 1) * TS;                                  // valid rows of the last tile (1 .. 64)
+    const int q_dead = Q - (TS / GKC) + (vlast + GKC - 1) / GKC;          // first stage of the last tile that is all padding
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<GNS - 2>();
         __syncthreads();
         issue(q + GNS - 1);
         const double *a = sm.S + (q % GNS) * GSLOT;
-        if (!stage_is_zero(q, tm)) tile_mma<false>(acc, a, same ? a : a + GCH, tm, 0, GKC);
+        if (stage_is_zero(q, tm) || q >= q_dead) continue;
+        // a diagonal tile of K^-1 is symmetric: warp w (rows 16w ..) only needs the columns up to its own diagonal block
+        if (same) tile_mma<false, 0xFF, true>(acc, a, a, tm, 0, GKC, 2 * warp + 2);
+        else tile_mma<false>(acc, a, a + GCH, tm, 0, GKC);
     }
     cp_async_wait<0>();
     __syncthreads();  // the ring is consumed: S parks the weights
     int gi[2];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
-    const double sym = same ? 1.0 : 2.0;
+    // weights of sum_{all i, j} W_ij dK_ij from the lower triangle alone: 2 below the diagonal, 1 on it, 0 above it
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
-        const double ai = sm.al[row_of(tm, mb)];
+        const int r = row_of(tm, mb);
+        const double ai = sm.al[r];
 #pragma unroll
-        for (int cc = 0; cc < NCC; ++cc) acc[mb][cc] = sym * fma(-ai, sm.al[TS + col_of(tm, cc)], acc[mb][cc]);
+        for (int cc = 0; cc < NCC; ++cc) {
+            const int cl = col_of(tm, cc);
+            const double sym = !same ? 2.0 : (cl < r ? 2.0 : (cl == r ? 1.0 : 0.0));
+            acc[mb][cc] = sym * fma(-ai, sm.al[TS + cl], acc[mb][cc]);
+        }
     }
     contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA);
     __syncthreads();

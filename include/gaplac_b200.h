@@ -101,7 +101,8 @@ int gpl_abi_version(void);
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
  * per-item kernel, 2 lockstep with the one-CTA-per-item potrf kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
- * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing) */
+ * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
+ * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);
 /* Optional per-call statistics.  With option "profile_events" = 1 the library brackets every
  * kernel launch of gpl_lml_batched(_dev) / gpl_lml_large with CUDA events (and synchronises the stream at the end of the
@@ -190,7 +191,8 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
  * Outputs, one record per kept transition (n_rec = n_samples, + n_adapt when record_warmup), chain-major:
  *   theta (p x n_rec x B), lp (n_rec x B; constrained-space log joint, Turing's `lp` column read by select --chains),
  *   q (dim x n_rec x B, optional), accept, eps (n_rec x B), depth, n_leapfrog, divergent (n_rec x B ints),
- *   status (B): 0 ok, 1 the initial point q0 has zero density, 2 not finished.  n_grad_evals: batched evaluations x B. */
+ *   status (B): 0 ok, 1 the initial point q0 has zero density, 2 not finished.  n_grad_evals: log-density + gradient
+ *   evaluations launched (one per active slot and leapfrog step; finished chains are compacted out of the batch). */
 typedef struct gpl_mcmc_opts {
     int32_t n_samples;     /* N of `--samples` (CLI/src/main.jl:65-71, default 200) */
     int32_t n_adapt;       /* warm-up transitions; < 0: min(1000, N / 2) as Turing's NUTS(0.65) */
