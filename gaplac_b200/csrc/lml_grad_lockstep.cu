@@ -152,7 +152,10 @@ __global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constan
 }
 
 // ---- tiles of K^-1 contracted with dK/dtheta --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 3) lk_gradc_kernel(const __grid_constant__ LkGradParams prm) {
+#ifndef GPL_GRADC_CTAS
+#define GPL_GRADC_CTAS 4  // 126 registers, no spills: four CTAs per SM like the other streaming kernels (150 registers at three)
+#endif
+__global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(const __grid_constant__ LkGradParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GradSmem &sm = *reinterpret_cast<GradSmem *>(smem_raw);
     const DevProgram &P = prm.prog;

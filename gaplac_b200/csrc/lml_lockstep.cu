@@ -490,10 +490,9 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
     }
     __syncthreads();  // item scalars
-    // Ragged n: a warp whose 16 rows all lie in the identity padding of the last tile row (i * 64 + r0 >= n) produces
-    // zeros whatever it multiplies; it keeps its share of the loads and barriers but issues no arithmetic
-    // (n = 300: a quarter of the last tile row, which is half of all the work below the diagonal).
-    const bool dead = i * TS + tm.r0 >= n;
+    // (Measured and dropped: letting the warps whose 16 rows lie entirely in the identity padding of the last tile row skip
+    // their arithmetic.  A CTA takes as long as its busiest warp, so n = 300 gained nothing, and the extra predicates in
+    // the update loop cost the headline shape 2 %.)
     double acc[2][NCC];
     {
         int gi[2];
@@ -502,8 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-        if (dead) acc_zero(acc);
-        else eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
+        eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
         __syncthreads();  // quarters read back: S is free for the ring
     }
 #pragma unroll
@@ -513,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         __syncthreads();
         issue(q + LK_NS - 1);
         const double *a = sm.S + (q % LK_NS) * LCH;
-        if (!dead) tile_mma<true>(acc, a, a + RCH, tm, 0, RKC);
+        tile_mma<true>(acc, a, a + RCH, tm, 0, RKC);
     }
     // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels; chunk c of L_jj is ring stage Q + c
 #pragma unroll
@@ -522,7 +520,6 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         __syncthreads();
         issue(Q + c + LK_NS - 1);  // nothing left to load: an empty group keeps the count in step
         const double *l = sm.S + ((Q + c) % LK_NS) * LCH;
-        if (dead) continue;
         if (c == 0) {
             trsm_rl_solve<0>(acc, sm.D, tm);
             trsm_rl_update<0>(acc, l, tm);
@@ -534,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
             trsm_rl_update<2>(acc, l, tm);
         }
     }
-    if (!dead) trsm_rl_solve<3>(acc, sm.D, tm);
+    trsm_rl_solve<3>(acc, sm.D, tm);
     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
     if (i == j + 1) {      // the tile just stored completes row j + 1: its diagonal tile can be formed now
         __syncthreads();   // the stores above are visible to the whole CTA; S is free
