@@ -466,7 +466,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- one process, all N devices, ONE C-ABI call (gpl_multi_lml_batched): what a Julia host would `ccall` ---------------
     multi = None
     if world > 1:
-        dist.barrier()
+        # the other ranks must wait on the HOST: an NCCL barrier spins a kernel on their GPUs, which rank 0 is about to use
+        host_group = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
         if rank == 0:
             try:
                 mwl = workload("c2", 0)
@@ -488,7 +491,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 mc.close()
             except Exception as e:          # never lose the headline line to the extra measurement
                 multi = {"error": repr(e)}
-        dist.barrier()
+        dist.barrier(group=host_group)
 
     out = None
     if rank == 0:
