@@ -452,8 +452,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             sfull = torch.cat([sg[r * m: r * m + sizes[r]] for r in range(world)]).cpu().numpy()
         else:
             sfull = sarm.dlml.cpu().numpy()
+        skms, _ = phase_times(sarm, flush, 2)
         entry = {"workload": swl["name"], "global_batch": Bg, "per_rank": hi - lo, "ms_per_step": s_ms,
-                 "library_ms": s_kern, "value": Bg / (s_ms * 1e-3), "unit": UNIT}
+                 "library_ms": s_kern, "value": Bg / (s_ms * 1e-3), "unit": UNIT,
+                 "per_kernel_ms_rank0": {nm: float(v) for nm, v in zip(PHASES, skms) if v > 0}}
         if rank == 0:
             idx = np.unique(np.linspace(0, Bg - 1, 8).astype(int))
             ref = cpu_lml(swl, idx, min(host_cores(), 8))

@@ -24,7 +24,7 @@ SYMBOLS = [
     "gpl_cov", "gpl_cov_dev", "gpl_cross_cov", "gpl_lml_batched", "gpl_lml_batched_dev", "gpl_posterior_fit",
     "gpl_posterior_free", "gpl_posterior_logpdf", "gpl_posterior_alpha", "gpl_posterior_factor",
     "gpl_posterior_mean_var", "gpl_sample", "gpl_chol_logdet", "gpl_chol_logdet_dev", "gpl_lml_large",
-    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream", "gpl_mcmc_nuts", "gpl_multi_init", "gpl_multi_destroy",
+    "gpl_predict_batched", "gpl_last_timing", "gpl_set_stream", "gpl_release_workspace", "gpl_mcmc_nuts", "gpl_multi_init", "gpl_multi_destroy",
     "gpl_multi_device_count", "gpl_multi_context", "gpl_multi_last_error", "gpl_multi_lml_batched", "gpl_multi_mcmc_nuts",
 ]
 
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.gpl_device_info.argtypes = [_vp, C.c_char_p, C.c_int, _ip, _ip]
     lib.gpl_last_timing.argtypes = [_vp, C.POINTER(GplTiming)]
     lib.gpl_set_stream.argtypes = [_vp, _vp]
+    lib.gpl_release_workspace.argtypes = [_vp]
     lib.gpl_multi_init.argtypes = [_ip, C.c_int, C.POINTER(_vp)]
     lib.gpl_multi_destroy.argtypes = [_vp]
     lib.gpl_multi_device_count.argtypes = [_vp]
@@ -339,6 +340,10 @@ class Context:
     def set_stream(self, stream: int = 0) -> None:
         """Host entry points run on this CUDA stream (raw cudaStream_t, e.g. torch.cuda.Stream.cuda_stream); 0 restores."""
         _check(self.h, load().gpl_set_stream(self.h, stream or None))
+
+    def release_workspace(self) -> None:
+        """Free the grow-only workspace (re-grown on demand)."""
+        _check(self.h, load().gpl_release_workspace(self.h))
 
     def last_timing(self):
         """(ms[7], launches[7]) per phase of the last call made with option profile_events = 1 (gpl_last_timing)."""

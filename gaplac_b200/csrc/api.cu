@@ -235,7 +235,6 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     if (!ctx->attr_lk) {
         CU(ctx, cudaFuncSetAttribute(lk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_below_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_step_smem_bytes()));
-        CU(ctx, cudaFuncSetAttribute(lk_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_potrf_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_potrf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)lk_potrf_warp_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_winv_smem_bytes()));
@@ -325,9 +324,7 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
                 mark(0);
             }
             pp.B = nb;
-            if (ctx->lml_variant == 2) {
-                lk_potrf_kernel<<<nb, NTHREADS, lk_potrf_smem_bytes(), st>>>(pp);  // one CTA per item (A/B reference)
-            } else {
+            {
                 // up to 7 GPs per CTA (one warp each); small batches are spread over the SMs instead
                 const int ipc_max = lk_potrf_warp_items_per_cta();
                 int ipc = (nb + ctx->sm_count - 1) / ctx->sm_count;
@@ -635,6 +632,24 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return GPL_OK;
+}
+
+// Give the grow-only workspace back (the buffers re-grow on the next call that needs them).
+int gpl_release_workspace(gpl_ctx *ctx) {
+    if (!ctx) return fail(ctx, GPL_ERR_ARG, "gpl_release_workspace: null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    std::vector<DevBuf *> bufs;
+    all_buffers(ctx, bufs);
+    for (DevBuf *b : bufs) {
+        if (b->p) cudaFree(b->p);
+        b->p = nullptr;
+        b->cap = 0;
+    }
+    for (auto &blk : ctx->postFree) cudaFree(blk.first);
+    ctx->postFree.clear();
     return GPL_OK;
 }
 

@@ -54,10 +54,8 @@ struct LkPotrfParams {
     int *info;
 };
 __global__ void lk_diag_kernel(const __grid_constant__ LkParams prm);        // grid B
-__global__ void lk_potrf_kernel(const __grid_constant__ LkPotrfParams prm);  // grid B
 __global__ void lk_below_kernel(const __grid_constant__ LkParams prm);       // grid B * (nt - 1 - j)
 size_t lk_step_smem_bytes();
-size_t lk_potrf_smem_bytes();
 __global__ void lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm);  // one warp per item
 size_t lk_potrf_warp_smem_bytes();
 int lk_potrf_warp_items_per_cta();

@@ -1,5 +1,5 @@
 // Batched log-marginal-likelihood, "lockstep" schedule: all GPs of the batch advance tile column by tile column
-// through three kernels per column, so that the latency-bound pivot chains of the diagonal tiles never share an SM
+// through two kernels per column, so that the latency-bound pivot chains of the diagonal tiles never share an SM
 // sub-partition with streams of tensor instructions.
 //
 // Why not one fused kernel per GP (lml_batched.cu)?  Measured on B200 (tools/pipe_mix.cu, profiles/README.md): a
@@ -14,7 +14,7 @@
 // Per tile column j (left-looking blocked Cholesky on 64 x 64 tiles, workspace = every item's lower tiles in HBM):
 //   lk_diag_kernel   grid B          T_jj = K_jj - sum_k L_jk L_jk'   (covariance tile generated in registers, DMMA
 //                                    update from the streamed tiles), y_j - sum_k L_jk z_k
-//   lk_potrf_kernel  grid B          L_jj = chol(T_jj), its four 16 x 16 block inverses, z_j, logdet and z'z partial sums
+//   lk_potrf_warp_kernel  one warp per item: L_jj = chol(T_jj), its four 16 x 16 block inverses, z_j, logdet and z'z sums
 //   lk_below_kernel  grid B*(nt-1-j) L_ij = (K_ij - sum_k L_ik L_jk') L_jj^-T   (K-gen, DMMA update, streamed solve)
 // The first and third kernel are pure throughput kernels (every phase saturates the FP64 pipe); the second is
 // latency-bound but runs thousands of independent chains with nothing else on the machine.
@@ -39,17 +39,6 @@ struct __align__(16) StepSmem {
     double zs[GPL_LK_ZMAX];  // z_k of the earlier tile columns (diag kernel)
 };
 
-struct __align__(16) PotrfSmem {
-    double S[TILE_ELEMS];
-    double D[DSIZE];
-    double rsbuf[16];
-    double pivbuf[TS];
-    double ybuf[TS];
-    double tmp16[16];
-    double L16s[256];
-    double red[NWARPS];
-};
-
 __device__ __forceinline__ const double *item_ptr(const double *base, long long stride, int b) {
     return base + (size_t)b * stride;
 }
@@ -57,7 +46,6 @@ __device__ __forceinline__ const double *item_ptr(const double *base, long long 
 }  // namespace
 
 size_t lk_step_smem_bytes() { return sizeof(StepSmem); }
-size_t lk_potrf_smem_bytes() { return sizeof(PotrfSmem); }
 
 // ---- diagonal tile of column j: covariance + update, right-hand side update ----------------------------------------
 // Only the lower triangle of a diagonal tile is needed (36 of its 64 8 x 8 blocks).  To balance them over the four
@@ -170,54 +158,6 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_diag_kernel(const __grid_const
     prepare_item_scalars(prm.prog, prm.Theta + (size_t)b * prm.p, &sm.sc, tid);
     __syncthreads();
     diag_tile_phase(prm, sm, prm.j, b, tid);
-}
-
-// ---- Cholesky of the diagonal tiles of column j -----------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 4) lk_potrf_kernel(const __grid_constant__ LkPotrfParams prm) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const TMap tm = thread_map(tid);
-    const int nt = prm.nt, j = prm.j, b = blockIdx.x;
-    const long long ntri = tri_index(nt, 0);
-    double *Tjj = prm.tiles + ((size_t)b * ntri + tri_index(j, j)) * TILE_ELEMS;
-    double *zb = prm.z + (size_t)b * nt * TS;
-    tile_load_async(sm.S, Tjj, tid);
-    cp_async_commit();
-    if (tid < TS) sm.ybuf[tid] = zb[j * TS + tid];
-    cp_async_wait<0>();
-    __syncthreads();
-    double acc[2][NCC];
-    acc_from_tile(acc, sm.S, tm);
-    __syncthreads();  // S becomes the factorisation scratch
-    const int cw = b & (NWARPS - 1);  // spread the pivot chains of co-resident CTAs over the SM sub-partitions
-    const int fail = tile_potrf(acc, tm, sm.S, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid, cw);
-    if (tid == cw * 32 && fail >= 0 && prm.info[b] == 0) prm.info[b] = j * TS + fail + 1;
-    __syncthreads();  // info[b] is read again below by thread 0
-    acc_to_tile(Tjj, acc, tm);
-    __syncthreads();  // scratch no longer read
-    acc_to_tile(sm.S, acc, tm);
-    tile_forward_solve(sm.S, sm.D, sm.ybuf, sm.tmp16, tid);  // z_j = L_jj^-1 (y_j - sum_k L_jk z_k)
-    double *Dg = prm.dblk + ((size_t)b * nt + j) * DSIZE;
-    for (int t = tid; t < DSIZE; t += NTHREADS) Dg[t] = sm.D[t];
-    double zq = 0.0, lg = 0.0;
-    if (tid < TS) {
-        const double z = sm.ybuf[tid];
-        zb[j * TS + tid] = z;
-        zq = z * z;
-        lg = log(sm.pivbuf[tid]);
-    }
-    zq = block_sum(zq, sm.red, tid);
-    lg = block_sum(lg, sm.red, tid);
-    if (tid == 0) {
-        const double q = (j ? prm.acc2[2 * b] : 0.0) + zq, l = (j ? prm.acc2[2 * b + 1] : 0.0) + lg;
-        prm.acc2[2 * b] = q;
-        prm.acc2[2 * b + 1] = l;
-        if (j == nt - 1) {
-            const int inf = prm.info[b];
-            prm.lml[b] = inf ? -INFINITY : -0.5 * ((double)prm.n * LOG2PI + l + q);
-        }
-    }
 }
 
 // ---- Cholesky of the diagonal tiles of column j, one WARP per GP ----------------------------------------------------------

@@ -95,12 +95,15 @@ int gpl_destroy(gpl_ctx *ctx);
  * context's own one; NULL restores it.  The calls stay blocking; a host that records CUDA events on its stream (or
  * orders other work on it, e.g. CUDA.jl's task stream) then sees the library's copies and kernels in that order. */
 int gpl_set_stream(gpl_ctx *ctx, void *stream);
+/* The context's workspace is grow-only (a 4096 x n=512 gradient batch holds ~11 GB): this releases all of it (and the
+ * recycled posterior blocks); the next call re-allocates what it needs.  Live posteriors are not touched. */
+int gpl_release_workspace(gpl_ctx *ctx);
 const char *gpl_last_error(gpl_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
 int gpl_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
- * per-item kernel, 2 lockstep with the one-CTA-per-item potrf kernel), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
+ * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
  * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
  * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);

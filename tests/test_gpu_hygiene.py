@@ -132,3 +132,13 @@ def test_device_entry_points_stay_inside_the_callers_buffers(ctx, n, B):
     assert int(info.abs().sum()) == 0 and int(ci[0]) == 0
     host = ctx.lml_batched(prog, X, y, Th, 0.1, grad=True)
     assert np.array_equal(lml.cpu().numpy(), host[0]) and np.array_equal(dy.cpu().numpy().reshape(B, n), host[3])
+
+
+def test_release_workspace_and_regrow(ctx):
+    d = W.make_c2(n=200, B=9)
+    prog = ctx.program(d["ops"])
+    a = ctx.lml_batched(prog, d["X"], d["y"], d["Theta"], 0.0, grad=True)
+    ctx.release_workspace()
+    b = ctx.lml_batched(prog, d["X"], d["y"], d["Theta"], 0.0, grad=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
