@@ -375,13 +375,13 @@ __device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const
 __device__ __forceinline__ void contract_grad_block(const DevProgram &P, const ItemScalars &S,
                                                     const double *__restrict__ X, int ldx, int n, const int (&gi)[2],
                                                     int cbase, int t, const double (&w)[2][16], double *scratch, int tid,
-                                                    double *gsum) {
+                                                    double *gsum, int hmax = 4) {  // quarters h >= hmax carry zero weights: skipped
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) scratch[(r * 16 + cc) * 128 + tid] = w[r][cc];
 #pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
+    for (int h = 0; h < hmax; ++h) {
         int gjh[4];
         double wq[8];
 #pragma unroll

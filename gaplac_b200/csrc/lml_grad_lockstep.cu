@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
             acc[mb][cc] = sym * fma(-ai, sm.al[TS + cl], acc[mb][cc]);
         }
     }
-    contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA);
+    // on a diagonal tile the 16-column quarters to the right of the warp's own diagonal block have zero weights
+    contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA, same ? warp + 1 : 4);
     __syncthreads();
     if (tid < prm.p) {
         double g = 0.0;
