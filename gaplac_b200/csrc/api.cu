@@ -21,7 +21,8 @@ namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 constexpr int PANEL = BIG_PANEL;  // tile columns per panel of the large-n factorisation (kernels.h)
-constexpr int SMALL_MAX_N = 512;  // posterior fits up to this n run on the one-CTA fused kernel
+constexpr int SMALL_MAX_N = 128;  // posterior fits up to this n run on the one-CTA fused kernel (n-sweep, profiles/sweep_large_r02.txt: the
+                                  // panel path is faster from n = 256 on: 0.21 vs 0.29 ms there, 0.38 vs 0.91 ms at n = 512)
 
 thread_local std::string g_last_error;
 
@@ -158,10 +159,16 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
                int y_batched, const double *dTheta, int p, const double *dsigma2, int sigma2_batched, double jitter,
                int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
                double *keep_ws, double *keep_vec, cudaStream_t st) {
-    if (!keep && ctx->lml_variant != 1)
+    const int nt = (n + TS - 1) / TS;
+    // One-tile models (n <= 64) in small batches - a single chain of the README workflow (n = 50), a handful of chains - are
+    // bound by launches, not by arithmetic: the fused per-item kernel evaluates value + gradient in ONE launch where the
+    // lockstep schedule needs six (diag, potrf, winv, alpha, gradc, gradsum); large batches of them lose nothing.
+    // The choice depends on n alone, not on the batch: an item's bits must not depend on how many items travel with it
+    // (chains sharded over devices or compacted out of a batch keep their values).  "lml_variant" = 3 forces lockstep.
+    const bool one_launch = want_grad && nt == 1 && ctx->lml_variant != 3;
+    if (!keep && ctx->lml_variant != 1 && !one_launch)
         return launch_lml_lockstep(ctx, prog, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
                                    dlml, dinfo, st, ddtheta, ddy, want_grad);
-    const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     const long long tiles_per_cta = ntri + nt + (want_grad ? ntri : 0);
     const size_t smem = lml_smem_bytes(want_grad != 0);
@@ -1381,9 +1388,9 @@ int gpl_mcmc_nuts(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const double
     const int saved_profile = ctx->profile_events;
     ctx->profile_events = 0;
     auto step = [&]() -> int {
-        int r = launch_lml_lockstep(ctx, prog->dev, n, d, xs, x_batched, c.latent ? dptr(o_ye) : ys, c.latent ? 1 : y_batched,
-                                    dptr(o_the), p, s2s, sigma2_batched, jitter, n_slots, dptr(o_lml), iptr(o_info), st,
-                                    dptr(o_dth), dptr(o_dy), 1);
+        int r = launch_lml(ctx, prog->dev, n, d, xs, x_batched, c.latent ? dptr(o_ye) : ys, c.latent ? 1 : y_batched, dptr(o_the), p,
+                           s2s, sigma2_batched, jitter, n_slots, dptr(o_lml), dptr(o_dth), dptr(o_dy), iptr(o_info), 1, 0, nullptr,
+                           nullptr, st);
         if (r) return r;
         mcmc_advance_kernel<<<warp_grid(n_slots), 32 * warps_per_block, 0, st>>>(mp);
         ctx->launches++;
