@@ -160,13 +160,10 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
                int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
                double *keep_ws, double *keep_vec, cudaStream_t st) {
     const int nt = (n + TS - 1) / TS;
-    // One-tile models (n <= 64) in small batches - a single chain of the README workflow (n = 50), a handful of chains - are
-    // bound by launches, not by arithmetic: the fused per-item kernel evaluates value + gradient in ONE launch where the
-    // lockstep schedule needs six (diag, potrf, winv, alpha, gradc, gradsum); large batches of them lose nothing.
-    // The choice depends on n alone, not on the batch: an item's bits must not depend on how many items travel with it
-    // (chains sharded over devices or compacted out of a batch keep their values).  "lml_variant" = 3 forces lockstep.
-    const bool one_launch = want_grad && nt == 1 && ctx->lml_variant != 3;
-    if (!keep && ctx->lml_variant != 1 && !one_launch)
+    // (Measured and dropped, tools/small_n_ab.py: sending value + gradient of one-tile models (n <= 64) to the fused per-item
+    // kernel - one launch instead of six.  45 vs 58 us for B <= 64, but 0.146 vs 0.110 ms at B = 1024 and 2.0 vs 1.3 ms at
+    // B = 16384: the README chain gains 11 %, every larger batch loses; an item's bits would also depend on the kernel choice.)
+    if (!keep && ctx->lml_variant != 1)
         return launch_lml_lockstep(ctx, prog, n, d, dX, x_batched, dY, y_batched, dTheta, p, dsigma2, sigma2_batched, jitter, B,
                                    dlml, dinfo, st, ddtheta, ddy, want_grad);
     const long long ntri = tri_index(nt, 0);

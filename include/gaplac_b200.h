@@ -102,9 +102,8 @@ const char *gpl_last_error(gpl_ctx *ctx); /* ctx may be NULL: last error of the 
 int gpl_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gpl_launch_count(gpl_ctx *ctx);
-/* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 default: lockstep schedule,
- * except value + gradient of one-tile models n <= 64, which take the one-launch fused per-item kernel; 1 fused per-item
- * kernel everywhere; 3 lockstep everywhere), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
+/* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
+ * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
  * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
  * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);

@@ -53,7 +53,8 @@ def main():
         K = torch.from_numpy(ctx.cov(prog, d["X"], d["theta"], 0.0)).to(dev)
         cs = ev(lambda: torch.linalg.cholesky(K))
         tf = n ** 3 / 3.0 / (f_ms * 1e-3) * 1e-12
-        path = "fused one-CTA kernel (fit)" if n <= 512 else "look-ahead panels + worker CTA" if n > 512 else ""
+        nt = (n + 63) // 64
+        path = "fused one-CTA kernel (fit)" if n <= 128 else ("panels on one stream" if (nt + 3) // 4 <= 2 else "look-ahead panels + worker CTA")
         print(f"{n:6d} {whole:13.3f} {f_ms:10.3f} {tf:6.2f} {100 * tf / 37.0:7.1f} {fit_ms:17.3f} {cs:18.3f} {n ** 3 / 3.0 / (cs * 1e-3) * 1e-12:6.2f}   {path}")
     ctx.set_stream(0)
     print("\nlml_large / posterior_fit: CUDA events on the library's stream around the blocking host-buffer calls (H2D of X, y and D2H of the "
