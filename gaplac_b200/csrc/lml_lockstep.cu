@@ -181,6 +181,18 @@ __device__ __forceinline__ int pw_y(int m) { return (32 + (m >> 4)) * TS + (m & 
 __device__ __forceinline__ int pw_piv(int m) { return (36 + (m >> 4)) * TS + (m & 15); }
 __device__ __forceinline__ int pw_rs(int c) { return 40 * TS + c; }
 size_t lk_potrf_warp_smem_bytes() { return sizeof(PotrfWarpSmem) * PW_WARPS; }  // per GP: / PW_WARPS
+// rows 16 P .. 63 of the 16 columns of panel P, shared tile -> workspace, 16 bytes per lane and step (P is a compile-time
+// constant: the chunk -> (column, offset) split is a multiply-shift, not the integer division it was)
+template <int P_>
+__device__ __forceinline__ void pw_store_panel(double *__restrict__ Tjj, const double *T, int lane) {
+    constexpr int cpc = 32 - 8 * P_;  // 16-byte chunks per column
+#pragma unroll
+    for (int it = 0; it < cpc / 2; ++it) {
+        const int q = it * 32 + lane, col = q / cpc, off = q - col * cpc;
+        const int e = (16 * P_ + col) * TS + 16 * P_ + 2 * off;
+        *reinterpret_cast<double2 *>(Tjj + e) = *reinterpret_cast<const double2 *>(T + e);
+    }
+}
 int lk_potrf_warp_items_per_cta() { return PW_WARPS; }
 
 __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const __grid_constant__ LkPotrfParams prm) {
@@ -265,34 +277,37 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 1) lk_potrf_warp_kernel(const _
         }
         __syncwarp();
         for (int e = lane; e < 256; e += 32) Dg[p * DBLK + (e >> 4) * DLD + (e & 15)] = sm.T[pw_w(e >> 4, e & 15)];
-        // rows below the block: L[r, panel] = T[r, panel] * W16'   (in place, one row per lane, two passes)
-        for (int r = 16 * (p + 1) + lane; r < TS; r += 32) {
-            double pk[16], out[16];
+        // rows below the block: L[rows, panel] = T[rows, panel] * W16' on the tensor path, 8 rows at a time, in place
+        // (ncu, round 2: the scalar version - one row per lane, 136 FMAs each - was 15 % of this kernel's instructions)
+        {
+            double bw[2][4];  // W16 as the column operand: bw[nb][kk] = W16[8 nb + g][4 kk + t]; rows 0..7 are zero beyond column 7
 #pragma unroll
-            for (int k = 0; k < 16; ++k) pk[k] = sm.T[tidx(r, 16 * p + k)];
+            for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                double s0 = 0.0, s1 = 0.0;
+                for (int kk = 0; kk < 4; ++kk) bw[nb][kk] = (nb == 0 && kk >= 2) ? 0.0 : sm.T[pw_w(8 * nb + g, 4 * kk + t)];
+            for (int rb = 2 * (p + 1); rb < 8; ++rb) {
+                double av[4], x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
 #pragma unroll
-                for (int k2 = 0; k2 <= c / 2; ++k2) {  // W16 row c is zero beyond column c
-                    const double2 w = *reinterpret_cast<const double2 *>(&sm.T[pw_w(c, 2 * k2)]);
-                    s0 = fma(pk[2 * k2], w.x, s0);
-                    s1 = fma(pk[2 * k2 + 1], w.y, s1);
-                }
-                out[c] = s0 + s1;
+                for (int kk = 0; kk < 4; ++kk) av[kk] = sm.T[tidx(8 * rb + g, 16 * p + 4 * kk + t)];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) dmma884(x0[0], x0[1], av[kk], bw[0][kk]);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) dmma884(x1[0], x1[1], av[kk], bw[1][kk]);
+                // every lane's operands are in registers before the (warp-synchronous) products: the stores cannot overtake a load
+                sm.T[tidx(8 * rb + g, 16 * p + 2 * t)] = x0[0];
+                sm.T[tidx(8 * rb + g, 16 * p + 2 * t + 1)] = x0[1];
+                sm.T[tidx(8 * rb + g, 16 * p + 8 + 2 * t)] = x1[0];
+                sm.T[tidx(8 * rb + g, 16 * p + 8 + 2 * t + 1)] = x1[1];
             }
-#pragma unroll
-            for (int c = 0; c < 16; ++c) sm.T[tidx(r, 16 * p + c)] = out[c];
         }
         if (p == 0) cp_async_wait<0>();  // panels 1..3 are needed from here on
         __syncwarp();
-        {  // panel p is final (L): rows 16p..63 of its columns go home now, spreading the stores over the kernel
-            const int cpc = 32 - 8 * p;
-            for (int q = lane; q < 16 * cpc; q += 32) {
-                const int col = q / cpc, off = q - col * cpc;
-                const int e = (16 * p + col) * TS + 16 * p + 2 * off;
-                *reinterpret_cast<double2 *>(Tjj + e) = *reinterpret_cast<const double2 *>(sm.T + e);
-            }
+        // panel p is final (L): rows 16p..63 of its columns go home now, spreading the stores over the kernel
+        switch (p) {
+        case 0: pw_store_panel<0>(Tjj, sm.T, lane); break;
+        case 1: pw_store_panel<1>(Tjj, sm.T, lane); break;
+        case 2: pw_store_panel<2>(Tjj, sm.T, lane); break;
+        default: pw_store_panel<3>(Tjj, sm.T, lane); break;
         }
         // right-hand side: z_p = W16 y_p, then y_below -= L[below, panel] z_p
         double zp = 0.0;
