@@ -53,14 +53,16 @@ struct gpl_ctx {
     std::mutex mu;
     int lml_variant = 0;
     int chol_variant = 0;
+    bool attr_sort = false;
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
     size_t lk_ws_limit = (size_t)24 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
+    int ou_separable = 1;                   // 1: sort the observations by the OU column and use the separable form (lockstep lml)
     int poison_ws = 0;                      // 1: fill the whole workspace with NaN payloads before every call (hygiene tests)
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
     int lk_launches[7] = {0, 0, 0, 0, 0, 0, 0};  // alpha / contraction kernels
     // grow-only device buffers
-    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart;
+    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart, lkPerm, lkXs, lkYs, lkDyS;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
 };
 
@@ -105,7 +107,7 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
 // records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
 inline void all_buffers(gpl_ctx *ctx, std::vector<DevBuf *> &out) {
     out = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
-           &ctx->lkM, &ctx->lkGpart, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
+           &ctx->lkM, &ctx->lkGpart, &ctx->lkPerm, &ctx->lkXs, &ctx->lkYs, &ctx->lkDyS, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
            &ctx->bLml, &ctx->bDtheta, &ctx->bDy, &ctx->bInfo, &ctx->bMisc, &ctx->bK, &ctx->bXs, &ctx->bMean, &ctx->bVar, &ctx->bWsV};
 }
 struct WsOrder {
@@ -154,7 +156,7 @@ int check_prog_args(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, int p) {
 int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
                         const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
                         int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st,
-                        double *ddtheta = nullptr, double *ddy = nullptr, int want_grad = 0);
+                        double *ddtheta = nullptr, double *ddy = nullptr, int want_grad = 0, int allow_sort = 1);
 int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched, const double *dY,
                int y_batched, const double *dTheta, int p, const double *dsigma2, int sigma2_batched, double jitter,
                int B, double *dlml, double *ddtheta, double *ddy, int *dinfo, int want_grad, int keep,
@@ -233,7 +235,7 @@ int launch_lml(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double 
 int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, const double *dX, int x_batched,
                         const double *dY, int y_batched, const double *dTheta, int p, const double *dsigma2,
                         int sigma2_batched, double jitter, int B, double *dlml, int *dinfo, cudaStream_t st,
-                        double *ddtheta, double *ddy, int want_grad) {
+                        double *ddtheta, double *ddy, int want_grad, int allow_sort) {
     const int nt = (n + TS - 1) / TS;
     const long long ntri = tri_index(nt, 0);
     if (!ctx->attr_lk) {
@@ -265,7 +267,45 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
         info_dev = ptr<int>(ctx->bInfo);
     }
     CU(ctx, cudaMemsetAsync(info_dev, 0, (size_t)B * sizeof(int), st));
+    // Separable OU leaves: when the program has one or two OU leaves on one input column and X is shared by the batch, the
+    // observations are sorted by that column first (lml, dtheta are invariant; dy is scattered back at the end): every
+    // block below the diagonal then has all its rows at or above all its columns and those leaves cost one multiply per
+    // entry instead of an exponential (kfun.cuh SepCtx).  Worth it only when there is enough work to pay for the sort.
+    int sep_col = -1;
+    if (ctx->ou_separable && allow_sort && !x_batched && nt >= 2 && n <= 8192 &&
+        ((long long)B * ntri >= 1024 || ctx->ou_separable == 2)) {  // 2: whatever the amount of work (tests)
+        int cnt = 0;
+        for (int f = 0; f < prog.n_factors; ++f)
+            if (prog.f[f].kind == F_OU) {
+                if (sep_col < 0) sep_col = prog.f[f].col;
+                if (prog.f[f].col == sep_col) ++cnt;
+            }
+        if (cnt < 1 || cnt > 2) sep_col = -1;
+    }
+    double *ddy_user = ddy;
+    if (sep_col >= 0) {
+        const size_t ny = (size_t)n * (y_batched ? B : 1);
+        if ((rc = ensure(ctx, ctx->lkPerm, (size_t)n * 4)) || (rc = ensure(ctx, ctx->lkXs, (size_t)n * d * 8)) ||
+            (rc = ensure(ctx, ctx->lkYs, ny * 8)) || (ddy && (rc = ensure(ctx, ctx->lkDyS, (size_t)n * B * 8))))
+            return rc;
+        int npow2 = 1;
+        while (npow2 < n) npow2 <<= 1;
+        const size_t sort_smem = (size_t)npow2 * 12;
+        if (!ctx->attr_sort) {
+            CU(ctx, cudaFuncSetAttribute(lk_sort_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+            ctx->attr_sort = true;
+        }
+        int *perm = ptr<int>(ctx->lkPerm);
+        lk_sort_perm_kernel<<<1, npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024, sort_smem, st>>>(dX + (size_t)sep_col * n, n, npow2, perm);
+        lk_permute_kernel<<<64, 256, 0, st>>>(dX, ptr<double>(ctx->lkXs), perm, n, d, 0);
+        lk_permute_kernel<<<ny > 65536 ? 592 : 64, 256, 0, st>>>(dY, ptr<double>(ctx->lkYs), perm, n, (long long)(ny / n), 0);
+        ctx->launches += 3;
+        dX = ptr<double>(ctx->lkXs);
+        dY = ptr<double>(ctx->lkYs);
+        if (ddy) ddy = ptr<double>(ctx->lkDyS);
+    }
     LkParams prm;
+    prm.sep_col = sep_col;
     prm.prog = prog;
     prm.n = n;
     prm.d = d;
@@ -369,6 +409,10 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
                 mark(6);
             }
         }
+    }
+    if (sep_col >= 0 && ddy_user) {  // dlml/dy back to the caller's order of the observations
+        lk_permute_kernel<<<592, 256, 0, st>>>(ddy, ddy_user, ptr<int>(ctx->lkPerm), n, B, 1);
+        ctx->launches++;
     }
     CU(ctx, cudaGetLastError());
     if (ctx->profile_events) {
@@ -675,6 +719,7 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
     else if (!strcmp(key, "profile_events")) ctx->profile_events = value;
     else if (!strcmp(key, "poison_ws")) ctx->poison_ws = value;
+    else if (!strcmp(key, "ou_separable")) ctx->ou_separable = value;
     else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
     return GPL_OK;
 }
@@ -1201,7 +1246,8 @@ int gpl_predict_batched(gpl_ctx *ctx, const gpl_prog *prog, int n, int d, const 
         const size_t s_off = sigma2_batched ? (size_t)off : 0;
         rc = launch_lml_lockstep(ctx, prog->dev, n, d, ptr<double>(ctx->bX), 0, ptr<double>(ctx->bY), 0,
                                  ptr<double>(ctx->bTheta) + (size_t)off * p, p, ptr<double>(ctx->bSigma) + s_off, sigma2_batched,
-                                 jitter, nb, ptr<double>(ctx->bLml) + off, ptr<int>(ctx->bInfo) + off, st);
+                                 jitter, nb, ptr<double>(ctx->bLml) + off, ptr<int>(ctx->bInfo) + off, st, nullptr, nullptr, 0,
+                                 /*allow_sort=*/0);  // the prediction kernels read X in the caller's order
         if (rc) return rc;
         LkPostParams pq;
         pq.nt = nt;

@@ -45,7 +45,12 @@ struct LkParams {
     double *tiles;  // B x ntri tiles (tile-major lower factor of every item)
     double *dblk;   // B x nt x DSIZE: block inverses of the diagonal tiles
     double *z;      // B x nt*64: right-hand side / z = L^-1 y
+    int sep_col;    // >= 0: X is sorted by this column; its OU leaves (at most two) use the separable form below the diagonal
 };
+// sorting the observations by one input column (the log marginal likelihood does not depend on their order)
+__global__ void lk_sort_perm_kernel(const double *xcol, int n, int npow2, int *perm);           // 1 CTA, bitonic
+// out[c*n + i] = in[c*n + perm[i]] (inverse: out[c*n + perm[i]] = in[c*n + i]) for c < ncols
+__global__ void lk_permute_kernel(const double *in, double *out, const int *perm, int n, long long ncols, int inverse);
 struct LkPotrfParams {
     int n, nt, j, B;
     double *tiles, *dblk, *z;

@@ -19,6 +19,17 @@ struct ItemScalars {
     double etab[64];             // 2^(j/64) for fast_exp (fastexp.h), copied from constant memory once per CTA
 };
 
+// Separable form of 1-D OU leaves for a 64 x 64 block whose rows all lie at or above its columns along the leaf's input
+// column (inputs sorted by that column, block below the diagonal):  exp(-|x_i - x_j| / l) = exp(-(x_i - c) / l) *
+// exp(-(c - x_j) / l)  for any c between the two groups - 128 exponentials per block instead of 4096, one multiply per
+// entry.  With c = the block's smallest row coordinate both exponents are <= 0 (no overflow).  u, v are filled by the
+// kernel that owns the block (lk_below_kernel); leaf[] lists the factor indices they stand for.
+struct SepCtx {
+    int n_sep;
+    int leaf[2];
+    double u[2][64], v[2][64];
+};
+
 static __constant__ double c_exptab[64] = {GPL_EXP_TABLE_VALUES};
 
 __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const double *__restrict__ theta,
@@ -66,7 +77,8 @@ template <int R, int C, bool SAME>
 __device__ __forceinline__ void leaf_block(const DevProgram &P, const ItemScalars &S, int f,
                                            const double *__restrict__ Xa, int lda, const int (&ci)[R],
                                            const double *__restrict__ Xb, int ldb, const int (&cj)[C],
-                                           const int (&gi)[R], const int (&gj)[C], double (&k)[R * C]) {
+                                           const int (&gi)[R], const int (&gj)[C], double (&k)[R * C],
+                                           const SepCtx *sep = nullptr) {
     const int kind = P.f[f].kind;
     if (kind == F_NOISE) {
 #pragma unroll
@@ -92,6 +104,16 @@ __device__ __forceinline__ void leaf_block(const DevProgram &P, const ItemScalar
             }
         fast_exp_vec<R * C>(k, S.etab);
     } else if (kind == F_OU) {
+        if (!SAME && sep) {  // block-uniform: the separable form, when this leaf has one (SepCtx above)
+            for (int q = 0; q < sep->n_sep; ++q)
+                if (sep->leaf[q] == f) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) k[r * C + c] = sep->u[q][gi[r] & 63] * sep->v[q][gj[c] & 63];
+                    return;
+                }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -116,7 +138,8 @@ __device__ __forceinline__ void leaf_block(const DevProgram &P, const ItemScalar
 template <int R, int C, bool SAME>
 __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalars &S, const double *__restrict__ Xa,
                                            int lda, int na, const int (&gi)[R], const double *__restrict__ Xb, int ldb,
-                                           int nb, const int (&gj)[C], double diag_add, double (&out)[R][C]) {
+                                           int nb, const int (&gj)[C], double diag_add, double (&out)[R][C],
+                                           const SepCtx *sep = nullptr) {
     int ci[R], cj[C];
 #pragma unroll
     for (int r = 0; r < R; ++r) ci[r] = gi[r] < na ? gi[r] : na - 1;
@@ -139,10 +162,10 @@ __device__ __forceinline__ void eval_block(const DevProgram &P, const ItemScalar
             continue;
         }
         double k[R * C];
-        leaf_block<R, C, SAME>(P, S, f0, Xa, lda, ci, Xb, ldb, cj, gi, gj, k);
+        leaf_block<R, C, SAME>(P, S, f0, Xa, lda, ci, Xb, ldb, cj, gi, gj, k, sep);
         for (int f = f0 + 1; f < f1; ++f) {
             double e[R * C];
-            leaf_block<R, C, SAME>(P, S, f, Xa, lda, ci, Xb, ldb, cj, gi, gj, e);
+            leaf_block<R, C, SAME>(P, S, f, Xa, lda, ci, Xb, ldb, cj, gi, gj, e, sep);
 #pragma unroll
             for (int q = 0; q < R * C; ++q) k[q] *= e[q];
         }
@@ -237,7 +260,7 @@ __device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const It
                                                    const double *__restrict__ Xa, int lda, int na, const int (&gi)[2],
                                                    const double *__restrict__ Xb, int ldb, int nb, int cbase, int t,
                                                    double diag_add, double *const (&slot)[NSLOT], int tid,
-                                                   double (&out)[2][16], int hmax = 4) {
+                                                   double (&out)[2][16], int hmax = 4, const SepCtx *sep = nullptr) {
     // CW = 4: the code runs per quarter (2 x 4 entries, 16 columns of the tile); CW = 8: per half (2 x 8 entries), which
     // halves the per-step interpretation / load / bookkeeping instructions and doubles the independent exp chains.
     static_assert(NSLOT == 1 || NSLOT == 2 || NSLOT == 4, "slots");
@@ -257,7 +280,7 @@ __device__ __forceinline__ void eval_block_acc_scr(const DevProgram &P, const It
 #pragma unroll
             for (int c = 0; c < CW; ++c) gjh[c] = cbase + 4 * CW * st + 8 * (c >> 1) + 2 * t + (c & 1);
             if (st < smax) {
-                eval_block<2, CW, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o);
+                eval_block<2, CW, SAME>(P, S, Xa, lda, na, gi, Xb, ldb, nb, gjh, diag_add, o, sep);
             } else {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)

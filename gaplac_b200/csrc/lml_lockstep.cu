@@ -37,6 +37,7 @@ struct __align__(16) StepSmem {
     double D[DSIZE];
     ItemScalars sc;
     double zs[GPL_LK_ZMAX];  // z_k of the earlier tile columns (diag kernel)
+    SepCtx sep;              // separable OU factors of the current block (lk_below_kernel, sorted inputs)
 };
 
 __device__ __forceinline__ const double *item_ptr(const double *base, long long stride, int b) {
@@ -445,6 +446,33 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
     }
     __syncthreads();  // item scalars
+    // Inputs sorted by column sep_col (the host sorted them: the likelihood does not depend on the order of the
+    // observations): every row of this block lies at or above every column, so the OU leaves on that column factor
+    // into row and column parts - one exponential per thread here instead of 32 per leaf in the evaluation below.
+    const SepCtx *sep = nullptr;
+    if (prm.sep_col >= 0) {
+        int ns = 0, lf[2] = {0, 0};
+        for (int f = 0; f < P.n_factors; ++f)
+            if (P.f[f].kind == F_OU && P.f[f].col == prm.sep_col && ns < 2) lf[ns++] = f;
+        const double *xc = X + (size_t)prm.sep_col * n;
+        const int loc = tid & (TS - 1);
+        const int r_first = i * TS < n ? i * TS : n - 1;
+        const double c0 = xc[r_first];  // smallest row coordinate of the block
+        const int idx = (tid < TS ? i : j) * TS + loc;
+        const double x = xc[idx < n ? idx : n - 1];
+        for (int q = 0; q < ns; ++q) {
+            const double a = sm.sc.a[lf[q]];  // -1 / l
+            if (tid < TS) sm.sep.u[q][loc] = fast_exp(a * (x - c0), sm.sc.etab);
+            else sm.sep.v[q][loc] = fast_exp(a * (c0 - x), sm.sc.etab);
+        }
+        if (tid == 0) {
+            sm.sep.n_sep = ns;
+            sm.sep.leaf[0] = lf[0];
+            sm.sep.leaf[1] = lf[1];
+        }
+        __syncthreads();
+        sep = &sm.sep;
+    }
     // (Measured and dropped: letting the warps whose 16 rows lie entirely in the identity padding of the last tile row skip
     // their arithmetic.  A CTA takes as long as its busiest warp, so n = 300 gained nothing, and the extra predicates in
     // the update loop cost the headline shape 2 %.)
@@ -456,7 +484,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-        eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc);
+        eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc, 4, sep);
         __syncthreads();  // quarters read back: S is free for the ring
     }
 #pragma unroll
@@ -491,6 +519,51 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     if (i == j + 1) {      // the tile just stored completes row j + 1: its diagonal tile can be formed now
         __syncthreads();   // the stores above are visible to the whole CTA; S is free
         diag_tile_phase(prm, sm, j + 1, b, tid);
+    }
+}
+
+// ---- sorting the observations by one input column -----------------------------------------------------------------------
+// One CTA, bitonic sort of (key, index) pairs in shared memory; ties keep no particular order (any order of equal
+// coordinates is a valid sort).  npow2 = n rounded up to a power of two (<= 8192); padding keys are +inf.
+__global__ void __launch_bounds__(1024) lk_sort_perm_kernel(const double *xcol, int n, int npow2, int *perm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *key = reinterpret_cast<double *>(smem_raw);
+    int *idx = reinterpret_cast<int *>(key + npow2);
+    for (int e = threadIdx.x; e < npow2; e += blockDim.x) {
+        const double v = e < n ? xcol[e] : INFINITY;
+        key[e] = v == v ? v : INFINITY;  // NaN coordinates sort last (the item's covariance is NaN whatever their place)
+        idx[e] = e;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int e = threadIdx.x; e < npow2; e += blockDim.x) {
+                const int o = e ^ jj;
+                if (o > e) {
+                    const bool up = (e & k) == 0;
+                    const double a = key[e], b = key[o];
+                    const int ia = idx[e], ib = idx[o];
+                    const bool gt = a > b || (a == b && ia > ib);  // index as tie-break: a strict total order
+                    if (gt == up) {
+                        key[e] = b;
+                        key[o] = a;
+                        idx[e] = ib;
+                        idx[o] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int e = threadIdx.x; e < n; e += blockDim.x) perm[e] = idx[e];
+}
+
+__global__ void lk_permute_kernel(const double *in, double *out, const int *perm, int n, long long ncols, int inverse) {
+    const long long total = (long long)n * ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long c = e / n;
+        const int i = (int)(e - c * n);
+        if (inverse) out[c * n + perm[i]] = in[e];
+        else out[e] = in[c * n + perm[i]];
     }
 }
 
