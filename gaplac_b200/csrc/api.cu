@@ -342,6 +342,7 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     gp.minv = ptr<double>(ctx->lkM);
     gp.alpha = ptr<double>(ctx->lkAlpha);
     gp.gpart = ptr<double>(ctx->lkGpart);
+    gp.sep_col = sep_col;
     auto mark = [&](int kind) {  // kind: 0 diag, 1 potrf, 2 below, 3..6 gradient phases (winv, minv, alpha, contraction), -1 start
         if (!ctx->profile_events) return;
         cudaEvent_t e;

@@ -84,6 +84,7 @@ struct LkGradParams {
     double *dtheta, *dy;             // outputs (dy may be NULL)
     const int *info;
     int B;
+    int sep_col;  // >= 0: X is sorted by this column (see LkParams): separable OU factors in the contraction below the diagonal
 };
 __global__ void lk_winv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * nt
 __global__ void lk_minv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * i  (row i, tiles j < i)

@@ -323,7 +323,10 @@ __device__ __forceinline__ void grad_reduce_add(double part, double *dst) {
 }
 __device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const ItemScalars &S,
                                                       const double *__restrict__ X, int ldx, int n, const int (&gi)[2],
-                                                      const int (&gj)[4], const double (&w)[8], double *gsum) {
+                                                      const int (&gj)[4], const double (&w)[8], double *gsum,
+                                                      const SepCtx *sep = nullptr) {
+    // sep != nullptr: a block below the diagonal on sorted inputs - cross form of the leaves (Noise = 0 there anyway) with
+    // the separable OU factors
     int ci[2], cj[4];
 #pragma unroll
     for (int r = 0; r < 2; ++r) ci[r] = gi[r] < n ? gi[r] : n - 1;
@@ -344,7 +347,8 @@ __device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const
         for (int e = 0; e < 8; ++e) wl[e] = wm[e];
         for (int f = f0; f < f1; ++f) {
             double k[8];
-            leaf_block<2, 4, true>(P, S, f, X, ldx, ci, X, ldx, cj, gi, gj, k);
+            if (sep) leaf_block<2, 4, false>(P, S, f, X, ldx, ci, X, ldx, cj, gi, gj, k, sep);
+            else leaf_block<2, 4, true>(P, S, f, X, ldx, ci, X, ldx, cj, gi, gj, k);
 #pragma unroll
             for (int e = 0; e < 8; ++e) wl[e] *= k[e];
         }
@@ -398,7 +402,8 @@ __device__ __forceinline__ void contract_grad_quarter(const DevProgram &P, const
 __device__ __forceinline__ void contract_grad_block(const DevProgram &P, const ItemScalars &S,
                                                     const double *__restrict__ X, int ldx, int n, const int (&gi)[2],
                                                     int cbase, int t, const double (&w)[2][16], double *scratch, int tid,
-                                                    double *gsum, int hmax = 4) {  // quarters h >= hmax carry zero weights: skipped
+                                                    double *gsum, int hmax = 4,  // quarters h >= hmax carry zero weights: skipped
+                                                    const SepCtx *sep = nullptr) {
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -413,7 +418,7 @@ __device__ __forceinline__ void contract_grad_block(const DevProgram &P, const I
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) wq[r * 4 + c] = scratch[(r * 16 + 4 * h + c) * 128 + tid];
-        contract_grad_quarter(P, S, X, ldx, n, gi, gjh, wq, gsum);
+        contract_grad_quarter(P, S, X, ldx, n, gi, gjh, wq, gsum, sep);
     }
 }
 

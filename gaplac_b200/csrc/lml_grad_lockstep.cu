@@ -41,6 +41,7 @@ struct __align__(16) GradSmem {
     ItemScalars sc;
     double al[2 * TS];  // alpha_i | alpha_j
     double gsum[NWARPS * GPL_MAX_THETA];
+    SepCtx sep;
 };
 
 // the first tile of a run is triangular: (M_jj)'(row, kk) = 0 for kk < row, so a warp whose rows start at r0 skips the
@@ -204,6 +205,29 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
     }
     cp_async_wait<0>();
     __syncthreads();  // the ring is consumed: S parks the weights
+    const SepCtx *sep = nullptr;
+    if (prm.sep_col >= 0 && !same) {  // sorted inputs, block below the diagonal: OU leaves on that column in separable form
+        int ns = 0, lf[2] = {0, 0};
+        for (int f = 0; f < P.n_factors; ++f)
+            if (P.f[f].kind == F_OU && P.f[f].col == prm.sep_col && ns < 2) lf[ns++] = f;
+        const double *xc = X + (size_t)prm.sep_col * n;
+        const int loc = tid & (TS - 1);
+        const double c0 = xc[i * TS < n ? i * TS : n - 1];
+        const int idx = (tid < TS ? i : j) * TS + loc;
+        const double x = xc[idx < n ? idx : n - 1];
+        for (int q = 0; q < ns; ++q) {
+            const double a = sm.sc.a[lf[q]];
+            if (tid < TS) sm.sep.u[q][loc] = fast_exp(a * (x - c0), sm.sc.etab);
+            else sm.sep.v[q][loc] = fast_exp(a * (c0 - x), sm.sc.etab);
+        }
+        if (tid == 0) {
+            sm.sep.n_sep = ns;
+            sm.sep.leaf[0] = lf[0];
+            sm.sep.leaf[1] = lf[1];
+        }
+        __syncthreads();
+        sep = &sm.sep;
+    }
     int gi[2];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) gi[mb] = i * TS + row_of(tm, mb);
@@ -220,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
         }
     }
     // on a diagonal tile the 16-column quarters to the right of the warp's own diagonal block have zero weights
-    contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA, same ? warp + 1 : 4);
+    contract_grad_block(P, sm.sc, X, n, n, gi, j * TS, tm.t, acc, sm.S, tid, sm.gsum + warp * GPL_MAX_THETA, same ? warp + 1 : 4, sep);
     __syncthreads();
     if (tid < prm.p) {
         double g = 0.0;
