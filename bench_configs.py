@@ -6,7 +6,7 @@ the stream the library runs on and checked against the CPU oracle on a sample (o
     golden         the reference's legacy fixture model, n=923, 200 chain rows (answers = the fixture's own values)
     C1             README workflow: one log-density + gradient call of the mcmc model body, n=50 (host-buffer ABI latency)
     C1 mcmc        the README command itself: gaplac mcmc "y ~| SqExp(:x)" --samples 500 on the device sampler (1 chain, and 64)
-    C3 mcmc        one chain per feature: 500 of the 2000 chains x n=300 in lockstep (50 draws after 100 warm-up: bounded sample)
+    C3 mcmc        one chain per feature: 256 of the 2000 chains x n=300 in lockstep (50 draws after 100 warm-up: bounded sample)
     C4             posterior fit n=2048 + mean/variance at 20 000 test points
     C5             single large GP n=8192: covariance build + blocked Cholesky + solve (gpl_lml_large)
 
@@ -109,7 +109,9 @@ def run_configs(ctx, dev, flush, quick: bool = False):
                 "seconds": res["seconds"], "samples_per_s": n_chains * res["n_samples"] / res["seconds"],
                 "transitions_per_s": n_chains * T / res["seconds"], "grad_evals": int(res["grad_evals"]),
                 "grad_evals_per_s": res["grad_evals"] / res["seconds"], "mean_accept": float(res["accept"].mean()),
-                "mean_tree_depth": float(res["depth"].mean()), "divergent_frac": float(res["divergent"].mean()),
+                "mean_tree_depth": float(res["depth"].mean()), "max_tree_depth": int(res["depth"].max()),
+                "divergent_frac": float(res["divergent"].mean()),
+                "leapfrogs_per_chain_mean_max": [float(res["n_leapfrog"].sum(axis=1).mean()), int(res["n_leapfrog"].sum(axis=1).max())],
                 "failed_chains": int((res["status"] != 0).sum()), "timing": "wall clock of the blocking call (H2D, graph replay of "
                 "(batched lml+gradient, chain state machine) per leapfrog step, D2H of the chains)", "note": note}
 
@@ -130,10 +132,10 @@ def run_configs(ctx, dev, flush, quick: bool = False):
     out["c1_mcmc"] = e
     r64 = mcmc.nuts(ctx, prog, d["X"], d["y"], [0.0], [20.0], sigma2=0.1, n_samples=500, seed=1, chains=64)
     out["c1_mcmc_64_chains"] = sampler_entry("C1 model, 64 chains x 500 samples in lockstep", r64, 64, 50, "same launches, 64 chains")
-    nch = 500
+    nch = 256
     r3 = mcmc.nuts(ctx, ctx.program(c3["ops"]), c3["X"], c3["Y"][:nch], [0.0, 0.0], [100.0, 2.0], sigma2=0.0, n_samples=50, n_adapt=100, seed=3)
     out["c3_mcmc"] = sampler_entry(f"C3 {nch} of the 2000 feature chains x n=300, Cat*SqExp+Noise, l ~ U(0,100), s2 ~ U(0,2): 50 draws + 100 warm-up each",
-                                   r3, nch, 300, "bounded sample of the config (a quarter of the features, short chains); finished chains are compacted out of the batch")
+                                   r3, nch, 300, "bounded sample of the config (an eighth of the features, short chains); finished chains are compacted out of the batch; the wall time of a lockstep batch is set by its slowest chain (deepest trees)")
 
     # ---- C4: posterior fit n=2048 + 20 000 test points (host-buffer ABI on torch's stream: CUDA events see it) -------------
     d = W.make_c4()
