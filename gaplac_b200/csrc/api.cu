@@ -270,10 +270,11 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     // Separable OU leaves: when the program has one or two OU leaves on one input column and X is shared by the batch, the
     // observations are sorted by that column first (lml, dtheta are invariant; dy is scattered back at the end): every
     // block below the diagonal then has all its rows at or above all its columns and those leaves cost one multiply per
-    // entry instead of an exponential (kfun.cuh SepCtx).  Worth it only when there is enough work to pay for the sort.
+    // entry instead of an exponential (kfun.cuh SepCtx).  The decision depends on the model alone (n, the program), never on
+    // the batch: an item's bits must not depend on how many items travel with it (parts of a multi-device call, the
+    // shrinking batch of the sampler).  From four tile columns on the three small launches of the sort cost < 5 % of a call.
     int sep_col = -1;
-    if (ctx->ou_separable && allow_sort && !x_batched && nt >= 2 && n <= 8192 &&
-        ((long long)B * ntri >= 1024 || ctx->ou_separable == 2)) {  // 2: whatever the amount of work (tests)
+    if (ctx->ou_separable && allow_sort && !x_batched && n <= 8192 && (nt >= 4 || (ctx->ou_separable == 2 && nt >= 2))) {
         int cnt = 0;
         for (int f = 0; f < prog.n_factors; ++f)
             if (prog.f[f].kind == F_OU) {

@@ -104,9 +104,9 @@ int gpl_abi_version(void);
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
  * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
- * "ou_separable" (default 1: batched log-densities whose program has one or two OU leaves on one column of a shared X sort
- * the observations by that column - the likelihood does not depend on their order; dy is returned in the caller's order -
- * and evaluate those leaves in separable form below the diagonal; 0: off),
+ * "ou_separable" (default 1: batched log-densities with n > 192 whose program has one or two OU leaves on one column of a
+ * shared X sort the observations by that column - the likelihood does not depend on their order; dy is returned in the
+ * caller's order - and evaluate those leaves in separable form below the diagonal; 0: off; 2: from n > 64 on),
  * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
  * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);

@@ -85,3 +85,30 @@ def test_headline_batch_uses_it_by_default(ctx):
     ref, _ = CO.lml_batched(d["ops"], d["X"], d["y"], d["Theta"][idx], 0.0)
     assert not info.any()
     assert np.max(np.abs(lml[idx] - ref) / np.abs(ref)) < 1e-9
+
+
+def test_bits_do_not_depend_on_the_batch(ctx):
+    """The separable path is chosen from the model alone (n, the program): an item evaluated alone, in a batch of 9, or in
+    one part of a two-part multi-device call has the same bits; so does a sampler chain run alone or among others."""
+    from gaplac_b200 import _lib, mcmc
+    d = W.make_c2(n=256, B=9)
+    prog = ctx.program(d["ops"])
+    whole = ctx.lml_batched(prog, d["X"], d["y"], d["Theta"], 0.0, grad=True)
+    alone = ctx.lml_batched(prog, d["X"], d["y"], d["Theta"][4:5], 0.0, grad=True)
+    for a, b in zip(whole, alone):
+        assert np.array_equal(a[4], b[0])
+    m = _lib.MultiContext([0, 0])
+    try:
+        parts = m.lml_batched(m.program(d["ops"]), d["X"], d["y"], d["Theta"], 0.0, grad=True)
+    finally:
+        m.close()
+    for a, b in zip(whole, parts):
+        assert np.array_equal(a, b)
+    # sampler on an OU model (marginal form: hyperparameters only), n = 256
+    lo, hi = np.array([0.2, 0.2, 0.01]), np.array([5.0, 5.0, 1.0])
+    kw = dict(sigma2=0.0, n_samples=3, n_adapt=4, seed=9, latent=False, record_warmup=True)
+    three = mcmc.nuts(ctx, prog, d["X"], d["y"], lo, hi, chains=3, **kw)
+    one = mcmc.nuts(ctx, prog, d["X"], d["y"], lo, hi, chains=1, chain_offset=1, **kw)
+    assert not three["status"].any()
+    for k in ("theta", "lp", "eps", "depth"):
+        assert np.array_equal(three[k][1], one[k][0]), k
