@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPL_ABI_VERSION 1
+#define GPL_ABI_VERSION 2 /* 2: + gpl_mcmc_nuts, gpl_multi_*, gpl_set_stream, gpl_last_timing, gpl_release_workspace */
 
 typedef enum gpl_status {
     GPL_OK = 0,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/gaplac_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.gpl_abi_version() == 1
+    assert lib.gpl_abi_version() == 2
 
 
 def test_gpl_op_layout_is_32_bytes():
