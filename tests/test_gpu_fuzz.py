@@ -111,3 +111,31 @@ def test_random_program_posterior_and_predictions(ctx, case):
         assert np.max(np.abs(bm[b] - rm)) < tol_m and np.max(np.abs(bv[b] - rv)) < tol_v
         if b == 0:
             assert np.max(np.abs(mean - rm)) < tol_m and np.max(np.abs(var - rv)) < tol_v
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_random_program_on_the_sorted_separable_path(ctx, case):
+    """n > 192 with at least one OU leaf: the library sorts the observations by the OU column and evaluates those leaves in
+    separable form below the diagonal (option ou_separable, on by default).  Same random formulas, several tile columns,
+    ties in the sorted column, per-item responses; lml, dtheta and dy (in the caller's order) against the oracle."""
+    rng = np.random.default_rng(5000 + case)
+    ops = _random_program(rng)
+    if not any(o.kind == OU for o in ops):
+        ops += [Op(OU, col=1, theta_slot=int(rng.integers(0, P_SLOTS)), var=0.5), Op(ADD)]
+    n = int(rng.choice([193, 200, 256, 257, 330]))
+    X = np.column_stack([rng.uniform(-3, 3, n), np.round(rng.uniform(0, 5, n), 2), rng.standard_normal(n),
+                         rng.integers(0, 4, n).astype(float)])
+    Y = rng.standard_normal((3, n))
+    Th = rng.uniform(0.4, 1.6, (3, P_SLOTS))
+    sigma2 = float(rng.uniform(0.3, 1.0))
+    try:
+        prog = ctx.program(ops)
+    except _lib.GaplacError:
+        return
+    lml, info, dth, dy = ctx.lml_batched(prog, X, Y, Th, sigma2, 1e-10, grad=True)
+    assert not info.any()
+    for b in range(3):
+        ref, rdth, rdy = O.lml_grad(ops, X, Y[b], Th[b], sigma2, 1e-10)
+        assert abs(lml[b] - ref) <= 1e-9 * abs(ref)
+        assert np.max(np.abs(dth[b] - rdth) / np.maximum(1.0, np.abs(rdth))) < 1e-8
+        assert np.max(np.abs(dy[b] - rdy)) < 1e-8 * max(1.0, np.max(np.abs(rdy)))
