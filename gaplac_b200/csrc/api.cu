@@ -506,10 +506,12 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)big_col_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(big_worker2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(ctx, cudaFuncSetAttribute(big_col2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_col_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
-    const size_t nflags = (size_t)BIG_MAXP + 3 * (size_t)nt + 1;  // ... + the abort flag of the bounded waits
+    const size_t nflags = (size_t)BIG_MAXP + 4 * (size_t)nt + 1;  // ... + the abort flag of the bounded waits + prep[nt]
     int rc = ensure(ctx, ctx->bigFlags, nflags * sizeof(int));
     if (rc) return rc;
     prm.flags = ptr<int>(ctx->bigFlags);
@@ -535,14 +537,16 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaMemsetAsync(prm.flags + P, 1, sizeof(int), ctx->s_panel));  // panel_ready[P]
         for (int j = k0; j < j1 && j + 1 < nt; ++j) {
             prm.j = j;
-            big_col_flag_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
+            if (ctx->chol_variant == 4) big_col_flag_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
+            else big_col2_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
             ctx->launches++;
         }
         return (int)GPL_OK;
     };
     if (use_worker) {
         CU(ctx, cudaStreamWaitEvent(ctx->s_worker, e0, 0));
-        big_worker_kernel<<<1, NTHREADS, diag_smem, ctx->s_worker>>>(prm);
+        if (ctx->chol_variant == 4) big_worker_kernel<<<1, NTHREADS, diag_smem, ctx->s_worker>>>(prm);  // round-1 protocol
+        else big_worker2_kernel<<<1, NTHREADS, diag_smem, ctx->s_worker>>>(prm);
         ctx->launches++;
         CU(ctx, cudaEventRecord(eW, ctx->s_worker));
         if ((rc = panel_cols(0))) return rc;

@@ -41,6 +41,7 @@ struct __align__(16) ColSmem {
     double Bt[TILE_ELEMS];
     double D[DSIZE];
     double ybuf[TS];
+    double tmp[16];
 };
 }  // namespace
 
@@ -359,6 +360,187 @@ __global__ void __launch_bounds__(NTHREADS, 4) big_col_flag_kernel(BigParams prm
         acc_to_tile(sm.A, acc, tm);
         wait_flag_ge(diagdone + j, 2, tid, abort_flag, prm.info);  // z_j (published after L_jj; normally long since)
         if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+        __syncthreads();
+        if (tid < TS) prm.y[i * TS + tid] = __ldcg(prm.y + i * TS + tid) - tile_row_dot(sm.A, sm.ybuf, tid, 0, TS);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int *>(rowdone + i) = j + 1;
+}
+
+
+// ---- look-ahead protocol, second version (round 2): the worker also solves tile (j+1, j) --------------------------------
+// In the first version every in-panel column cost a round trip on the serial path: worker factors L_jj -> the column CTA
+// of row j+1 loads it, solves its tile, stores, raises a flag -> the worker loads that tile back, applies the last update
+// and factors again (measured: 23.8 us of worker work + 8.5 us of waiting per column).  Here the CTA of row j+1 prepares,
+// while the worker is still busy with L_jj, everything that does not need L_jj - the tile (j+1, j) and the diagonal tile
+// (j+1, j+1), both updated with the panel's earlier columns - and raises prep[j+1]; the worker then solves the one tile
+// itself (it has L_jj and its block inverses in shared memory), stores it, and applies the rank-64 update to the diagonal
+// tile it keeps in registers for the next factorisation: no hand-off remains on the path inside a panel.  The forward
+// solves z_j = L_jj^-1 y_j move off the worker to that same CTA (the last column's stays with the worker).  At a panel
+// boundary (column j+1 starts a new panel: its tiles still await the trailing update) the column CTA of row j+1 solves its
+// tile as before.
+//   prep[i] = j + 1: T'_{i,j} and T'_{i,i} (i = j + 1) are stored          (written by big_col2_kernel, read by the worker)
+//   tiledone[i] = j + 1: L_{i,j} is stored  (by the worker for i = j + 1 inside a panel, by big_col2_kernel otherwise)
+__global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+    const int tid = threadIdx.x, nt = prm.nt;
+    const TMap tm = thread_map(tid);
+    int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
+    int *abort_flag = tiledone + nt, *prep = abort_flag + 1;
+    constexpr int PANEL_ = BIG_PANEL;
+    double acc[2][NCC];
+    bool have_acc = false;  // acc already holds the fully updated diagonal tile of this column
+    for (int j = 0; j < nt; ++j) {
+        const int k0 = (j / PANEL_) * PANEL_, j1 = (k0 + PANEL_ < nt) ? k0 + PANEL_ : nt;
+        double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
+        if (!have_acc) {  // first column of a panel: the trailing kernels have applied every earlier panel
+            wait_flag_ge(panel_ready + j / PANEL_, 1, tid, abort_flag, prm.info);
+            tile_load_async(sm.A, Tjj, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            acc_from_tile(acc, sm.A, tm);
+            __syncthreads();  // sm.A becomes the factorisation scratch
+        }
+        const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+        if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
+        acc_to_tile(Tjj, acc, tm);
+        for (int t = tid; t < DSIZE; t += NTHREADS) prm.dblk[(size_t)j * DSIZE + t] = sm.D[t];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;  // the solves below the tile can start
+        if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
+        have_acc = false;
+        if (j + 1 < j1) {  // same panel: tile (j+1, j) and the next diagonal tile are this CTA's business
+            const int i = j + 1;
+            double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
+            wait_flag_ge(prep + i, j + 1, tid, abort_flag, prm.info);
+            tile_load_async(sm.Bt, Tij, tid);
+            tile_load_async(sm.W, prm.tiles + tri_index(i, i) * TILE_ELEMS, tid);
+            cp_async_commit();
+            acc_to_tile(sm.A, acc, tm);  // L_jj for the solve (the scratch is dead: barrier above)
+            cp_async_wait<0>();
+            __syncthreads();
+            double t2[2][NCC];
+            acc_from_tile(t2, sm.Bt, tm);
+            tile_trsm_ld(t2, sm.A, sm.D, tm);  // L_{j+1,j} = T'_{j+1,j} L_jj^-T
+            acc_to_tile(Tij, t2, tm);
+            __syncthreads();  // every thread has read its part of sm.Bt: it now takes L_{j+1,j} for the update
+            acc_to_tile(sm.Bt, t2, tm);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile int *>(tiledone + i) = j + 1;
+            acc_from_tile(acc, sm.W, tm);                    // T'_{j+1,j+1}: updated with the panel's columns before j
+            tile_mma<true>(acc, sm.Bt, sm.Bt, tm, 0, TS);    // ... and now with column j
+            __syncthreads();  // sm.A (next scratch), sm.Bt, sm.W are free again
+            have_acc = true;
+        }
+    }
+    if (prm.y) {  // z of the last column: no column kernel exists for it
+        const int j = nt - 1;
+        acc_to_tile(sm.A, acc, tm);
+        if (j > 0) wait_flag_ge(rowdone + j, j, tid, abort_flag, prm.info);
+        else __syncthreads();
+        if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+        tile_forward_solve(sm.A, sm.D, sm.ybuf, sm.rsbuf, tid);
+        if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 2;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) big_col2_kernel(BigParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ColSmem &sm = *reinterpret_cast<ColSmem *>(smem_raw);
+    const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
+    const TMap tm = thread_map(tid);
+    int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt, *abort_flag = tiledone + nt;
+    int *prep = abort_flag + 1;
+    const bool next_diag = (i == j + 1);
+    const bool same_panel = next_diag && (j + 1 < prm.j1);  // the worker solves this tile
+    double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
+    tile_load_async(sm.A, Tij, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][NCC];
+    acc_from_tile(acc, sm.A, tm);
+    // in-panel update: tiles (i, k) and (j, k), k0 <= k < j, were final before this kernel was launched (stream order)
+    for (int k = prm.k0; k < j; ++k) {
+        __syncthreads();
+        tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+        tile_load_async(sm.Bt, prm.tiles + tri_index(j, k) * TILE_ELEMS, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_mma<true>(acc, sm.A, sm.Bt, tm, 0, TS);
+    }
+    if (same_panel) {
+        acc_to_tile(Tij, acc, tm);  // T'_{j+1,j}: everything but the solve
+        // the diagonal tile of column j + 1 with the updates of the panel's columns before j
+        double *Tii = prm.tiles + tri_index(i, i) * TILE_ELEMS;
+        __syncthreads();
+        tile_load_async(sm.A, Tii, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        acc_from_tile(acc, sm.A, tm);
+        for (int k = prm.k0; k < j; ++k) {
+            __syncthreads();
+            tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            tile_mma<true>(acc, sm.A, sm.A, tm, 0, TS);
+        }
+        acc_to_tile(Tii, acc, tm);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(prep + i) = j + 1;
+    }
+    wait_flag_ge(diagdone + j, 1, tid, abort_flag, prm.info);  // L_jj and its block inverses are stored
+    __syncthreads();
+    tile_load_async(sm.Bt, prm.tiles + tri_index(j, j) * TILE_ELEMS, tid);
+    block_load_async<DSIZE * 8>(sm.D, prm.dblk + (size_t)j * DSIZE, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!same_panel) {
+        tile_trsm_ld(acc, sm.Bt, sm.D, tm);
+        acc_to_tile(Tij, acc, tm);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(tiledone + i) = j + 1;
+    }
+    if (prm.y) {
+        if (next_diag) {  // this CTA owns the forward solve of column j: z_j = L_jj^-1 y_j
+            if (j > 0) wait_flag_ge(rowdone + j, j, tid, abort_flag, prm.info);  // y_j carries every earlier column
+            if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+            tile_forward_solve(sm.Bt, sm.D, sm.ybuf, sm.tmp, tid);
+            if (tid < TS) prm.y[j * TS + tid] = sm.ybuf[tid];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 2;
+        } else {
+            wait_flag_ge(diagdone + j, 2, tid, abort_flag, prm.info);
+            if (tid < TS) sm.ybuf[tid] = __ldcg(prm.y + j * TS + tid);
+        }
+    }
+    if (same_panel) {  // the worker stores L_{j+1,j}: wait for it (also orders this kernel's end behind that store)
+        wait_flag_ge(tiledone + i, j + 1, tid, abort_flag, prm.info);
+        if (prm.y) {
+            tile_load_async(sm.A, Tij, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+    } else if (prm.y) {
+        __syncthreads();
+        acc_to_tile(sm.A, acc, tm);
+    }
+    if (prm.y) {
         __syncthreads();
         if (tid < TS) prm.y[i * TS + tid] = __ldcg(prm.y + i * TS + tid) - tile_row_dot(sm.A, sm.ybuf, tid, 0, TS);
     }

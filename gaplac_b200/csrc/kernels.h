@@ -168,7 +168,7 @@ struct BigParams {
     int k0;         // first tile column of the current panel (left-looking inside the panel)
     int j1;         // trailing update: one past the last tile column of the finished panel
     int l0, l1;     // trailing update: tile columns [l0, l1) are updated by this launch (all rows i >= l)
-    int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] | tiledone[nt] (device ints)
+    int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] | tiledone[nt] | abort | prep[nt]
 };
 constexpr int BIG_MAXP = 64;  // panels the flag block has room for
 #ifndef GPL_BIG_PANEL
@@ -181,6 +181,8 @@ __global__ void big_trail_kernel(BigParams prm);  // one CTA per trailing tile (
 // look-ahead protocol: one persistent CTA factors every diagonal tile in turn; the column kernel waits for it per column
 __global__ void big_worker_kernel(BigParams prm);    // 1 CTA for the whole factorisation (owns an SM)
 __global__ void big_col_flag_kernel(BigParams prm);
+__global__ void big_worker2_kernel(BigParams prm);  // second version: the worker also solves tile (j+1, j) inside a panel
+__global__ void big_col2_kernel(BigParams prm);
 __global__ void big_winv_kernel(BigParams prm);  // grid nt: W_jj = L_jj^-1 from L_jj and its block inverses  // nt - j - 1 CTAs; spins on diagdone[j], publishes rowdone[i]
 size_t big_smem_bytes();
 size_t big_col_smem_bytes();

@@ -103,7 +103,8 @@ int gpl_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
- * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path), "lk_ws_limit_mb" (workspace cap, default 24576),
+ * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path; 2: its one-stream form; 3: look-ahead streams without the worker CTA;
+ * 4: the round-1 worker protocol), "lk_ws_limit_mb" (workspace cap, default 24576),
  * "ou_separable" (default 1: batched log-densities with n > 192 whose program has one or two OU leaves on one column of a
  * shared X sort the observations by that column - the likelihood does not depend on their order; dy is returned in the
  * caller's order - and evaluate those leaves in separable form below the diagonal; 0: off; 2: from n > 64 on),

@@ -205,7 +205,7 @@ def test_gradient_mcmc_model_body(ctx):
 
 
 # ---------------------------------------------------------------------------------------------- posterior / predict / sample
-@pytest.mark.parametrize("n,variant", [(50, 0), (130, 0), (300, 0), (130, 1), (700, 0)])
+@pytest.mark.parametrize("n,variant", [(50, 0), (130, 0), (300, 0), (130, 1), (700, 0), (700, 4), (1000, 0), (1000, 3)])
 def test_posterior_and_predict_match_oracle(ctx, n, variant):
     X, y = _data(n, seed=30 + n)
     Xs, _ = _data(150, seed=77)
