@@ -511,7 +511,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaFuncSetAttribute(big_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const bool use_worker = NP <= BIG_MAXP && nt <= 140 && ctx->chol_variant != 3;
-    const size_t nflags = (size_t)BIG_MAXP + 4 * (size_t)nt + 1;  // ... + the abort flag of the bounded waits + prep[nt]
+    const size_t nflags = (size_t)BIG_MAXP + 5 * (size_t)nt + 1;  // ... + the abort flag of the bounded waits + prep[nt] + prepd[nt]
     int rc = ensure(ctx, ctx->bigFlags, nflags * sizeof(int));
     if (rc) return rc;
     prm.flags = ptr<int>(ctx->bigFlags);
@@ -538,7 +538,8 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         for (int j = k0; j < j1 && j + 1 < nt; ++j) {
             prm.j = j;
             if (ctx->chol_variant == 4) big_col_flag_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
-            else big_col2_kernel<<<nt - j - 1, NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
+            else  // + one CTA that prepares the next diagonal tile when column j + 1 lies in the same panel
+                big_col2_kernel<<<nt - j - 1 + (j + 1 < j1 ? 1 : 0), NTHREADS, big_col_smem_bytes(), ctx->s_panel>>>(prm);
             ctx->launches++;
         }
         return (int)GPL_OK;

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
     const int tid = threadIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
     int *panel_ready = prm.flags, *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt;
-    int *abort_flag = tiledone + nt, *prep = abort_flag + 1;
+    int *abort_flag = tiledone + nt, *prep = abort_flag + 1, *prepd = prep + nt;
     constexpr int PANEL_ = BIG_PANEL;
     double acc[2][NCC];
     bool have_acc = false;  // acc already holds the fully updated diagonal tile of this column
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
         if (j + 1 < j1) {  // same panel: tile (j+1, j) and the next diagonal tile are this CTA's business
             const int i = j + 1;
             double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
-            wait_flag_ge(prep + i, j + 1, tid, abort_flag, prm.info);
+            wait_flag_ge(prep + i, j + 1, tid, abort_flag, prm.info);   // T'_{j+1,j} is stored (row CTA of the column kernel)
+            wait_flag_ge(prepd + i, j + 1, tid, abort_flag, prm.info);  // T'_{j+1,j+1} is stored (its extra CTA)
             tile_load_async(sm.Bt, Tij, tid);
             tile_load_async(sm.W, prm.tiles + tri_index(i, i) * TILE_ELEMS, tid);
             cp_async_commit();
@@ -458,7 +459,32 @@ __global__ void __launch_bounds__(NTHREADS, 3) big_col2_kernel(BigParams prm) {
     const int tid = threadIdx.x, j = prm.j, i = prm.j + 1 + blockIdx.x, nt = prm.nt;
     const TMap tm = thread_map(tid);
     int *rowdone = prm.flags + BIG_MAXP, *diagdone = rowdone + nt, *tiledone = diagdone + nt, *abort_flag = tiledone + nt;
-    int *prep = abort_flag + 1;
+    int *prep = abort_flag + 1, *prepd = prep + nt;
+    if (i == nt) {  // the extra CTA of an in-panel column: the diagonal tile of column j + 1 with the updates of the panel's
+                    // columns before j (the row CTA prepares the tile (j+1, j) meanwhile: the two together take as long
+                    // as the worker's factorisation of L_jj, either alone fits inside it)
+        const int r = j + 1;
+        double *Trr = prm.tiles + tri_index(r, r) * TILE_ELEMS;
+        tile_load_async(sm.A, Trr, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double d[2][NCC];
+        acc_from_tile(d, sm.A, tm);
+        for (int k = prm.k0; k < j; ++k) {
+            __syncthreads();
+            tile_load_async(sm.A, prm.tiles + tri_index(r, k) * TILE_ELEMS, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            tile_mma<true>(d, sm.A, sm.A, tm, 0, TS);
+        }
+        acc_to_tile(Trr, d, tm);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int *>(prepd + r) = j + 1;
+        return;
+    }
     const bool next_diag = (i == j + 1);
     const bool same_panel = next_diag && (j + 1 < prm.j1);  // the worker solves this tile
     double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
@@ -480,23 +506,6 @@ __global__ void __launch_bounds__(NTHREADS, 3) big_col2_kernel(BigParams prm) {
     }
     if (same_panel) {
         acc_to_tile(Tij, acc, tm);  // T'_{j+1,j}: everything but the solve
-        // the diagonal tile of column j + 1 with the updates of the panel's columns before j
-        double *Tii = prm.tiles + tri_index(i, i) * TILE_ELEMS;
-        __syncthreads();
-        tile_load_async(sm.A, Tii, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        acc_from_tile(acc, sm.A, tm);
-        for (int k = prm.k0; k < j; ++k) {
-            __syncthreads();
-            tile_load_async(sm.A, prm.tiles + tri_index(i, k) * TILE_ELEMS, tid);
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
-            tile_mma<true>(acc, sm.A, sm.A, tm, 0, TS);
-        }
-        acc_to_tile(Tii, acc, tm);
         __threadfence();
         __syncthreads();
         if (tid == 0) *reinterpret_cast<volatile int *>(prep + i) = j + 1;

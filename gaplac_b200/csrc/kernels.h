@@ -168,7 +168,7 @@ struct BigParams {
     int k0;         // first tile column of the current panel (left-looking inside the panel)
     int j1;         // trailing update: one past the last tile column of the finished panel
     int l0, l1;     // trailing update: tile columns [l0, l1) are updated by this launch (all rows i >= l)
-    int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] | tiledone[nt] | abort | prep[nt]
+    int *flags;     // look-ahead worker protocol: panel_ready[BIG_MAXP] | rowdone[nt] | diagdone[nt] | tiledone[nt] | abort | prep[nt] | prepd[nt]
 };
 constexpr int BIG_MAXP = 64;  // panels the flag block has room for
 #ifndef GPL_BIG_PANEL
