@@ -392,19 +392,31 @@ __global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
     constexpr int PANEL_ = BIG_PANEL;
     double acc[2][NCC];
     bool have_acc = false;  // acc already holds the fully updated diagonal tile of this column
+#ifdef GPL_BIG_PROFILE
+    long long w_panel = 0, w_load = 0, w_potrf = 0, w_pub = 0, w_prep = 0, w_solve = 0, w_begin = clock64(), w_t;
+#define W_MARK(acc_) do { const long long now_ = clock64(); acc_ += now_ - w_t; w_t = now_; } while (0)
+#else
+#define W_MARK(acc_)
+#endif
     for (int j = 0; j < nt; ++j) {
+#ifdef GPL_BIG_PROFILE
+        w_t = clock64();
+#endif
         const int k0 = (j / PANEL_) * PANEL_, j1 = (k0 + PANEL_ < nt) ? k0 + PANEL_ : nt;
         double *Tjj = prm.tiles + tri_index(j, j) * TILE_ELEMS;
         if (!have_acc) {  // first column of a panel: the trailing kernels have applied every earlier panel
             wait_flag_ge(panel_ready + j / PANEL_, 1, tid, abort_flag, prm.info);
+            W_MARK(w_panel);
             tile_load_async(sm.A, Tjj, tid);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
             acc_from_tile(acc, sm.A, tm);
             __syncthreads();  // sm.A becomes the factorisation scratch
+            W_MARK(w_load);
         }
         const int fail = tile_potrf(acc, tm, sm.A, sm.L16s, sm.D, sm.rsbuf, sm.pivbuf, tid);
+        W_MARK(w_potrf);
         if (tid == 0 && fail >= 0) atomicCAS(prm.info, 0, j * TS + fail + 1);
         acc_to_tile(Tjj, acc, tm);
         for (int t = tid; t < DSIZE; t += NTHREADS) prm.dblk[(size_t)j * DSIZE + t] = sm.D[t];
@@ -412,12 +424,14 @@ __global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
         __syncthreads();
         if (tid == 0) *reinterpret_cast<volatile int *>(diagdone + j) = 1;  // the solves below the tile can start
         if (tid < TS) prm.pivlog[j * TS + tid] = log(sm.pivbuf[tid]);
+        W_MARK(w_pub);
         have_acc = false;
         if (j + 1 < j1) {  // same panel: tile (j+1, j) and the next diagonal tile are this CTA's business
             const int i = j + 1;
             double *Tij = prm.tiles + tri_index(i, j) * TILE_ELEMS;
             wait_flag_ge(prep + i, j + 1, tid, abort_flag, prm.info);   // T'_{j+1,j} is stored (row CTA of the column kernel)
             wait_flag_ge(prepd + i, j + 1, tid, abort_flag, prm.info);  // T'_{j+1,j+1} is stored (its extra CTA)
+            W_MARK(w_prep);
             tile_load_async(sm.Bt, Tij, tid);
             tile_load_async(sm.W, prm.tiles + tri_index(i, i) * TILE_ELEMS, tid);
             cp_async_commit();
@@ -436,9 +450,15 @@ __global__ void __launch_bounds__(NTHREADS) big_worker2_kernel(BigParams prm) {
             acc_from_tile(acc, sm.W, tm);                    // T'_{j+1,j+1}: updated with the panel's columns before j
             tile_mma<true>(acc, sm.Bt, sm.Bt, tm, 0, TS);    // ... and now with column j
             __syncthreads();  // sm.A (next scratch), sm.Bt, sm.W are free again
+            W_MARK(w_solve);
             have_acc = true;
         }
     }
+#ifdef GPL_BIG_PROFILE
+    if (tid == 0)
+        printf("worker2: total %lld clk: waiting for panel_ready %lld, loading first tiles %lld, potrf %lld, publish %lld, waiting for prep %lld, "
+               "solve + update %lld\n", clock64() - w_begin, w_panel, w_load, w_potrf, w_pub, w_prep, w_solve);
+#endif
     if (prm.y) {  // z of the last column: no column kernel exists for it
         const int j = nt - 1;
         acc_to_tile(sm.A, acc, tm);
