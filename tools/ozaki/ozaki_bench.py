@@ -44,13 +44,13 @@ def sync(what):
 
 
 def ozaki(A, C, S, mode, ws=None):
-    """C (row-major view with unit column stride) -= / = A A^T on lower-triangle 128x128 tiles."""
+    """C (column-major view: unit row stride) -= / = A A^T on lower-triangle 128x128 tiles; A row-major."""
     n, K = A.shape
-    assert A.stride(1) == 1 and C.stride(1) == 1
+    assert A.stride(1) == 1 and C.stride(0) == 1
     if ws is None:
         ws = torch.empty(lib.ozaki_ws_bytes(n, K, S), dtype=torch.uint8, device="cuda")
     check(lib.ozaki_split(A.data_ptr(), A.stride(0), n, K, S, ws.data_ptr(), stream()), "split")
-    check(lib.ozaki_update(n, K, S, ws.data_ptr(), C.data_ptr(), C.stride(0), mode, stream()), "update")
+    check(lib.ozaki_update(n, K, S, ws.data_ptr(), C.data_ptr(), C.stride(1), mode, stream()), "update")
     return ws
 
 
@@ -68,6 +68,14 @@ def split_emulated(A, S):
         r = r - q
         qs.append(q)
     return torch.exp2(e), qs
+
+
+def colmajor(n, m, fill=None):
+    """An n x m FP64 matrix stored column-major (what LAPACK and the product's tiles use)."""
+    t = torch.empty(m, n, dtype=torch.float64, device="cuda").t()
+    if fill is not None:
+        t.fill_(fill)
+    return t
 
 
 def lower_tiles_mask(n):
@@ -103,7 +111,7 @@ def exactness(out):
                 grp = sum(qs[s] @ qs[g - s].T for s in range(g + 1))
                 want += grp * 2.0 ** (-7 * (g + 2))
             want = want * rs[:, None] * rs[None, :]
-            C = torch.full((n, n), 7.0, dtype=torch.float64, device="cuda")
+            C = colmajor(n, n, 7.0)
             ozaki(A, C, S, 1)
             sync(f"exact n={n} K={K} S={S}")
             diff = ((C - want) * mask).abs().max().item()
@@ -111,7 +119,7 @@ def exactness(out):
             print(f"exact  n={n:5d} K={K:4d} S={S}  max |kernel - emulation| = {diff:.3e}  (|C| max {want.abs().max().item():.3e})", flush=True)
         ref = A @ A.T
         for S in (5, 6, 7, 8):
-            C = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+            C = colmajor(n, n, 0.0)
             ozaki(A, C, S, 1)
             sync(f"fp64 n={n} K={K} S={S}")
             nrm = A.norm(dim=1)
@@ -120,7 +128,8 @@ def exactness(out):
             print(f"fp64   n={n:5d} K={K:4d} S={S}  max |C - A A^T| / (|a_i| |a_j|) = {err:.3e}", flush=True)
         # mode 0 subtracts in place
         C0 = torch.randn(n, n, dtype=torch.float64, device="cuda")
-        C = C0.clone()
+        C = colmajor(n, n)
+        C.copy_(C0)
         ozaki(A, C, 8, 0)
         sync("mode 0")
         err = ((C - (C0 - ref)) * mask).abs().max().item() / ref.abs().max().item()
@@ -134,7 +143,7 @@ def speed(out, quick):
     shapes = [(8192, 512)] if quick else [(8192, 512), (8192, 1024), (4096, 512), (8192, 256)]
     for (n, K) in shapes:
         A = torch.randn(n, K, dtype=torch.float64, device="cuda")
-        C = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+        C = colmajor(n, n, 0.0)
         flops = (n // 128) * (n // 128 + 1) / 2 * 2 * 128 * 128 * K  # the lower-triangle tiles actually computed
         t_gemm = time_ms(lambda: torch.addmm(C, A, A.T, beta=1.0, alpha=-1.0, out=C))
         row = dict(n=n, K=K, dgemm_full_ms=t_gemm, dgemm_tf=2.0 * n * n * K / t_gemm * 1e-9)
@@ -142,7 +151,7 @@ def speed(out, quick):
         for S in (8, 7, 6, 5):
             ws = torch.empty(lib.ozaki_ws_bytes(n, K, S), dtype=torch.uint8, device="cuda")
             t_split = time_ms(lambda: check(lib.ozaki_split(A.data_ptr(), A.stride(0), n, K, S, ws.data_ptr(), stream()), "split"))
-            t_upd = time_ms(lambda: check(lib.ozaki_update(n, K, S, ws.data_ptr(), C.data_ptr(), C.stride(0), 0, stream()), "update"))
+            t_upd = time_ms(lambda: check(lib.ozaki_update(n, K, S, ws.data_ptr(), C.data_ptr(), C.stride(1), 0, stream()), "update"))
             sync("speed")
             pairs = S * (S + 1) // 2
             row[f"S{S}"] = dict(split_ms=t_split, update_ms=t_upd, fp64_equiv_tf=flops / (t_split + t_upd) * 1e-9,
@@ -156,7 +165,8 @@ def speed(out, quick):
 def chol_blocked(Kmat, y, nb, S):
     """Right-looking blocked Cholesky; S = 0 uses cuBLAS FP64 for the trailing update, S > 0 the INT8 split."""
     n = Kmat.shape[0]
-    A = Kmat.clone()
+    A = colmajor(n, n)
+    A.copy_(Kmat)
     ws = None
     for p in range(0, n, nb):
         e = min(p + nb, n)
