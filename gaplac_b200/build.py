@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libgaplac_b200.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-format-truncation"]
-CU_SOURCES = ["api.cu", "lml_batched.cu", "lml_lockstep.cu", "lml_grad_lockstep.cu", "mcmc.cu", "kbuild.cu", "big.cu", "predict.cu"]
+CU_SOURCES = ["api.cu", "lml_batched.cu", "lml_lockstep.cu", "lml_grad_lockstep.cu", "mcmc.cu", "kbuild.cu", "big.cu", "trail_int8.cu", "predict.cu"]
 CPP_SOURCES = ["program.cpp", "multi.cpp"]
 
 

@@ -40,8 +40,8 @@ struct gpl_ctx {
     char name[128] = {0};
     cudaStream_t stream = nullptr;      // the stream host entry points run on (own_stream, or the caller's: gpl_set_stream)
     cudaStream_t own_stream = nullptr;
-    cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr;  // look-ahead streams of the large-n factorisation
-    DevBuf bigFlags, bigD, lkW, lkAlpha, dStage;
+    cudaStream_t s_panel = nullptr, s_trail = nullptr, s_worker = nullptr, s_i8 = nullptr;  // look-ahead streams of the large-n factorisation
+    DevBuf bigFlags, bigD, lkW, lkAlpha, dStage, i8Slices, i8Scale;
     void *hStage = nullptr;  // pinned host staging block of the small-call path (gpl_lml_batched)
     std::vector<gpl_post *> livePosts;  // posteriors created on this context and not yet freed (gpl_destroy detaches them)
     cudaEvent_t wsEvent = nullptr;      // completion of the last call that used the shared workspace (any stream)
@@ -57,6 +57,8 @@ struct gpl_ctx {
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
     size_t lk_ws_limit = (size_t)24 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
     int ou_separable = 1;                   // 1: sort the observations by the OU column and use the separable form (lockstep lml)
+    int trail_int8 = -1;                    // large-n trailing updates: -1 auto (INT8 split path, 8 slices, from n = 8192 on), 0 FP64 DMMA only,
+                                            // 5..9: that many slices from n = 4096 on
     int poison_ws = 0;                      // 1: fill the whole workspace with NaN payloads before every call (hygiene tests)
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
@@ -106,7 +108,7 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
 // caller's stream): every call that touches the workspace first makes its stream wait for the previous such call and
 // records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
 inline void all_buffers(gpl_ctx *ctx, std::vector<DevBuf *> &out) {
-    out = {&ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
+    out = {&ctx->i8Slices, &ctx->i8Scale, &ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
            &ctx->lkM, &ctx->lkGpart, &ctx->lkPerm, &ctx->lkXs, &ctx->lkYs, &ctx->lkDyS, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
            &ctx->bLml, &ctx->bDtheta, &ctx->bDy, &ctx->bInfo, &ctx->bMisc, &ctx->bK, &ctx->bXs, &ctx->bMean, &ctx->bVar, &ctx->bWsV};
 }
@@ -503,6 +505,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_worker, cudaStreamNonBlocking, hi));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_panel, cudaStreamNonBlocking, hi));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, lo));
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_i8, cudaStreamNonBlocking, lo));
         CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)big_col_smem_bytes()));
@@ -544,6 +547,25 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         }
         return (int)GPL_OK;
     };
+    // Option "trail_int8" (S slices): the update of everything beyond the current block of I8_BLOCK tile columns is deferred
+    // until the block is complete and then applied in one pass on the INT8 tensor path (K = 1024); inside the block the
+    // panels are applied with DMMA as before.  One SM stays with the worker CTA.
+    int i8S = 0;
+    if (I8_BLOCK % PANEL == 0) {
+        if (ctx->trail_int8 > 0 && nt >= 4 * I8_BLOCK) i8S = ctx->trail_int8;
+        else if (ctx->trail_int8 < 0 && nt >= 8 * I8_BLOCK) i8S = 8;  // measured break-even: n = 6144 level, n = 8192 1.2x, n = 16384 1.65x
+    }
+    int *i8dbg = nullptr;
+    if (i8S && i8_prepare()) {
+        if (ctx->trail_int8 > 0) return fail(ctx, GPL_ERR_CUDA, "INT8 trailing update: kernels or cuTensorMapEncodeTiled unavailable");
+        i8S = 0;  // automatic mode: stay on the FP64 tensor path
+    }
+    if (i8S) {
+        if ((rc = ensure(ctx, ctx->i8Slices, i8_slices_bytes(nt, I8_BLOCK, I8_BLOCK, i8S)))) return rc;
+        if ((rc = ensure(ctx, ctx->i8Scale, i8_scale_bytes(nt, I8_BLOCK) + 4 * sizeof(int)))) return rc;
+        i8dbg = reinterpret_cast<int *>(ptr<char>(ctx->i8Scale) + i8_scale_bytes(nt, I8_BLOCK));
+        CU(ctx, cudaMemsetAsync(i8dbg, 0, 4 * sizeof(int), st));
+    }
     if (use_worker) {
         CU(ctx, cudaStreamWaitEvent(ctx->s_worker, e0, 0));
         if (ctx->chol_variant == 4) big_worker_kernel<<<1, NTHREADS, diag_smem, ctx->s_worker>>>(prm);  // round-1 protocol
@@ -555,9 +577,57 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         factor_panel(0, ctx->s_panel, diag_smem);
     }
     CU(ctx, cudaEventRecord(eF[0], ctx->s_panel));
+    int sms = 0;
+    CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    int i8_ctas = (sms * 2) / 3;  // persistent CTAs of the deferred part; the next block's chain and DMMA updates get the rest
+    if (const char *e = getenv("GPL_I8_CTAS")) i8_ctas = atoi(e);
+    bool have_i8 = false;
+    cudaEvent_t eSplit = nullptr, eI8 = nullptr;
+    if (i8S) {
+        CU(ctx, cudaEventCreateWithFlags(&eSplit, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&eI8, cudaEventDisableTiming));
+        CU(ctx, cudaStreamWaitEvent(ctx->s_i8, e0, 0));
+    }
     for (int P = 0; P + 1 < NP; ++P) {
         const int n0 = (P + 1) * PANEL, n1 = (n0 + PANEL < nt) ? n0 + PANEL : nt;  // columns of panel P + 1
+        const int blk_end = i8S ? ((P * PANEL) / I8_BLOCK + 1) * I8_BLOCK : nt;  // DMMA updates stop at the end of the block
         if (P >= 1) CU(ctx, cudaStreamWaitEvent(ctx->s_panel, eB[P - 1], 0));
+        if (i8S && n0 >= blk_end && n0 < nt) {
+            // panel P closes a block: slices of its rows below, then three INT8 passes in the order the chain needs them --
+            // the columns of the next panel at once (all SMs but the worker's, on the chain's stream), the other columns of
+            // the next block on the DMMA stream (ordered with the in-block updates of the same tiles that follow), the rest
+            // of the trailing matrix on its own stream while the next block is being factored on the remaining SMs
+            const int c0 = blk_end - I8_BLOCK, ncb = (nt - blk_end + 1) / 2;
+            const int cb_a = PANEL / 2 < ncb ? PANEL / 2 : ncb, cb_b = I8_BLOCK / 2 < ncb ? I8_BLOCK / 2 : ncb;
+            signed char *sl = ptr<signed char>(ctx->i8Slices);
+            double *sc = ptr<double>(ctx->i8Scale);
+            if (have_i8) CU(ctx, cudaStreamWaitEvent(ctx->s_panel, eI8, 0));  // the slices and the tiles of the previous pass
+            if (i8_split_tiles(tiles, nt, blk_end, c0, I8_BLOCK, i8S, sl, sc, ctx->s_panel)) return fail(ctx, GPL_ERR_CUDA, "i8_split_tiles launch failed");
+            CU(ctx, cudaEventRecord(eSplit, ctx->s_panel));
+            int irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, 0, cb_a, sms - 1, dinfo, i8dbg, ctx->s_panel);
+            CU(ctx, cudaStreamWaitEvent(ctx->s_trail, eSplit, 0));
+            if (!irc && cb_a < cb_b) {
+                irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, cb_a, cb_b, i8_ctas, dinfo, i8dbg, ctx->s_trail);
+                ctx->launches++;
+            }
+            CU(ctx, cudaEventRecord(eB[P], ctx->s_trail));
+            if (!irc && cb_b < ncb) {
+                CU(ctx, cudaStreamWaitEvent(ctx->s_i8, eB[P], 0));  // one persistent INT8 kernel at a time next to the chain
+                irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, cb_b, ncb, i8_ctas, dinfo, i8dbg, ctx->s_i8);
+                ctx->launches++;
+            }
+            CU(ctx, cudaEventRecord(eI8, ctx->s_i8));
+            have_i8 = true;
+            if (irc) return fail(ctx, GPL_ERR_CUDA, "INT8 trailing update: launch failed (%d)", irc);
+            ctx->launches += 2;
+            if (use_worker) {
+                if ((rc = panel_cols(P + 1))) return rc;
+            } else {
+                factor_panel(P + 1, ctx->s_panel, diag_smem);
+            }
+            CU(ctx, cudaEventRecord(eF[P + 1], ctx->s_panel));
+            continue;
+        }
         trail(P, n0, n1, ctx->s_panel);
         if (use_worker) {
             if ((rc = panel_cols(P + 1))) return rc;
@@ -566,9 +636,10 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         }
         CU(ctx, cudaEventRecord(eF[P + 1], ctx->s_panel));
         CU(ctx, cudaStreamWaitEvent(ctx->s_trail, eF[P], 0));
-        trail(P, n1, nt, ctx->s_trail);
+        trail(P, n1, n1 > blk_end ? n1 : (blk_end < nt ? blk_end : nt), ctx->s_trail);
         CU(ctx, cudaEventRecord(eB[P], ctx->s_trail));
     }
+    if (have_i8) CU(ctx, cudaStreamWaitEvent(st, eI8, 0));
     CU(ctx, cudaStreamWaitEvent(st, eF[NP - 1], 0));
     CU(ctx, cudaStreamWaitEvent(st, eB[NP - 2], 0));
     if (use_worker) {
@@ -579,6 +650,11 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     CU(ctx, cudaGetLastError());
     if (ctx->profile_events == 2) {  // debug: when each panel was factored / its trailing update finished (ms from start)
         CU(ctx, cudaStreamSynchronize(st));
+        if (i8dbg) {
+            int h[4] = {0, 0, 0, 0};
+            cudaMemcpy(h, i8dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "int8 trailing update: barrier breadcrumb (code, cta, parity, failed) = %d %d %d %d\n", h[0], h[1], h[2], h[3]);
+        }
         for (int P = 0; P < NP; ++P) {
             float tf = 0.f, tb = 0.f;
             cudaEventElapsedTime(&tf, e0, eF[P]);
@@ -592,6 +668,8 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(eW);
+    if (eSplit) cudaEventDestroy(eSplit);
+    if (eI8) cudaEventDestroy(eI8);
     return GPL_OK;
 }
 
@@ -685,6 +763,7 @@ int gpl_destroy(gpl_ctx *ctx) {
     if (ctx->s_worker) cudaStreamDestroy(ctx->s_worker);
     if (ctx->s_panel) cudaStreamDestroy(ctx->s_panel);
     if (ctx->s_trail) cudaStreamDestroy(ctx->s_trail);
+    if (ctx->s_i8) cudaStreamDestroy(ctx->s_i8);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return GPL_OK;
@@ -726,6 +805,10 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
     else if (!strcmp(key, "profile_events")) ctx->profile_events = value;
     else if (!strcmp(key, "poison_ws")) ctx->poison_ws = value;
+    else if (!strcmp(key, "trail_int8")) {
+        if (value != 0 && value != -1 && (value < 5 || value > 9)) return fail(ctx, GPL_ERR_ARG, "trail_int8: -1 (auto), 0 (off) or 5..9 slices");
+        ctx->trail_int8 = value;
+    }
     else if (!strcmp(key, "ou_separable")) ctx->ou_separable = value;
     else return fail(ctx, GPL_ERR_ARG, "gpl_set_option: unknown key '%s'", key);
     return GPL_OK;

@@ -188,6 +188,17 @@ size_t big_smem_bytes();
 size_t big_col_smem_bytes();
 size_t big_trail_smem_bytes();
 
+// ---- trailing update on the INT8 tensor path (trail_int8.cu; option "trail_int8") ------------------------------------------
+constexpr int I8_BLOCK = 16;  // tile columns per deferred update: K = 1024
+int i8_prepare();  // loads the kernels; must run before a spinning persistent kernel is resident
+size_t i8_slices_bytes(int nt, int t0, int kt, int S);
+size_t i8_scale_bytes(int nt, int t0);
+// rows of L below tile row t0, tile columns [c0, c0 + kt) -> S slices (K-major) + row scales
+int i8_split_tiles(const double *tiles, int nt, int t0, int c0, int kt, int S, signed char *slices, double *rowscale, cudaStream_t st);
+// tiles(i, l) -= L_i L_l^T over those columns, for the 128-wide column blocks [cb0, cb1) of the region starting at t0
+int i8_trail(double *tiles, int nt, int t0, int kt, int S, const signed char *slices, const double *rowscale, int cb0, int cb1,
+             int max_ctas, int *info, int *dbg, cudaStream_t st);
+
 // backward substitution alpha = L^-T z, one launch per tile row i (descending), grid = i + 1 CTAs; r = z on entry
 // of the first launch and is updated in place, alpha receives the finished blocks
 __global__ void big_backward_kernel(const double *tiles, const double *winv, int i, double *r, double *alpha);
