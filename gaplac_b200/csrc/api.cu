@@ -504,7 +504,7 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
         CU(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_worker, cudaStreamNonBlocking, hi));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_panel, cudaStreamNonBlocking, hi));
-        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, lo));
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->s_trail, cudaStreamNonBlocking, hi < lo - 1 ? lo - 1 : lo));
         CU(ctx, cudaStreamCreateWithPriority(&ctx->s_i8, cudaStreamNonBlocking, lo));
         CU(ctx, cudaFuncSetAttribute(big_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(ctx, cudaFuncSetAttribute(big_col_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -550,20 +550,20 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     // Option "trail_int8" (S slices): the update of everything beyond the current block of I8_BLOCK tile columns is deferred
     // until the block is complete and then applied in one pass on the INT8 tensor path (K = 1024); inside the block the
     // panels are applied with DMMA as before.  One SM stays with the worker CTA.
+    constexpr int i8_block = I8_BLOCK;  // tile columns per deferred INT8 pass (B200 sweep, n = 8192: 8 -> 6.5 ms, 16 -> 6.35, 32 -> 6.6)
+    static_assert(I8_BLOCK % BIG_PANEL == 0 && I8_BLOCK % 2 == 0, "blocks are whole panels and whole 128-column blocks");
     int i8S = 0;
-    if (I8_BLOCK % PANEL == 0) {
-        if (ctx->trail_int8 > 0 && nt >= 4 * I8_BLOCK) i8S = ctx->trail_int8;
-        else if (ctx->trail_int8 < 0 && nt >= 8 * I8_BLOCK) i8S = 8;  // measured break-even: n = 6144 level, n = 8192 1.2x, n = 16384 1.65x
-    }
+    if (ctx->trail_int8 > 0 && nt >= 4 * i8_block) i8S = ctx->trail_int8;
+    else if (ctx->trail_int8 < 0 && nt >= 8 * i8_block) i8S = 8;  // measured: n = 6144 level with DMMA, n = 8192 1.2x, n = 16384 1.65x
     int *i8dbg = nullptr;
     if (i8S && i8_prepare()) {
         if (ctx->trail_int8 > 0) return fail(ctx, GPL_ERR_CUDA, "INT8 trailing update: kernels or cuTensorMapEncodeTiled unavailable");
         i8S = 0;  // automatic mode: stay on the FP64 tensor path
     }
     if (i8S) {
-        if ((rc = ensure(ctx, ctx->i8Slices, i8_slices_bytes(nt, I8_BLOCK, I8_BLOCK, i8S)))) return rc;
-        if ((rc = ensure(ctx, ctx->i8Scale, i8_scale_bytes(nt, I8_BLOCK) + 4 * sizeof(int)))) return rc;
-        i8dbg = reinterpret_cast<int *>(ptr<char>(ctx->i8Scale) + i8_scale_bytes(nt, I8_BLOCK));
+        if ((rc = ensure(ctx, ctx->i8Slices, i8_slices_bytes(nt, i8_block, i8_block, i8S)))) return rc;
+        if ((rc = ensure(ctx, ctx->i8Scale, i8_scale_bytes(nt, i8_block) + 4 * sizeof(int)))) return rc;
+        i8dbg = reinterpret_cast<int *>(ptr<char>(ctx->i8Scale) + i8_scale_bytes(nt, i8_block));
         CU(ctx, cudaMemsetAsync(i8dbg, 0, 4 * sizeof(int), st));
     }
     if (use_worker) {
@@ -579,8 +579,9 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     CU(ctx, cudaEventRecord(eF[0], ctx->s_panel));
     int sms = 0;
     CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    int i8_ctas = (sms * 2) / 3;  // persistent CTAs of the deferred part; the next block's chain and DMMA updates get the rest
-    if (const char *e = getenv("GPL_I8_CTAS")) i8_ctas = atoi(e);
+    // persistent CTAs of the deferred passes; the next block's chain and DMMA updates get the rest (B200 sweep, n = 8192:
+    // 64 -> 7.0 ms, 98 -> 6.35, 128 -> 6.55; one output block per CTA instead of persistent CTAs: 6.6; profiles/i8_trail_r02.txt)
+    const int i8_ctas = (sms * 2) / 3;
     bool have_i8 = false;
     cudaEvent_t eSplit = nullptr, eI8 = nullptr;
     if (i8S) {
@@ -590,30 +591,30 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     }
     for (int P = 0; P + 1 < NP; ++P) {
         const int n0 = (P + 1) * PANEL, n1 = (n0 + PANEL < nt) ? n0 + PANEL : nt;  // columns of panel P + 1
-        const int blk_end = i8S ? ((P * PANEL) / I8_BLOCK + 1) * I8_BLOCK : nt;  // DMMA updates stop at the end of the block
+        const int blk_end = i8S ? ((P * PANEL) / i8_block + 1) * i8_block : nt;  // DMMA updates stop at the end of the block
         if (P >= 1) CU(ctx, cudaStreamWaitEvent(ctx->s_panel, eB[P - 1], 0));
         if (i8S && n0 >= blk_end && n0 < nt) {
             // panel P closes a block: slices of its rows below, then three INT8 passes in the order the chain needs them --
             // the columns of the next panel at once (all SMs but the worker's, on the chain's stream), the other columns of
             // the next block on the DMMA stream (ordered with the in-block updates of the same tiles that follow), the rest
             // of the trailing matrix on its own stream while the next block is being factored on the remaining SMs
-            const int c0 = blk_end - I8_BLOCK, ncb = (nt - blk_end + 1) / 2;
-            const int cb_a = PANEL / 2 < ncb ? PANEL / 2 : ncb, cb_b = I8_BLOCK / 2 < ncb ? I8_BLOCK / 2 : ncb;
+            const int c0 = blk_end - i8_block, ncb = (nt - blk_end + 1) / 2;
+            const int cb_a = PANEL / 2 < ncb ? PANEL / 2 : ncb, cb_b = i8_block / 2 < ncb ? i8_block / 2 : ncb;
             signed char *sl = ptr<signed char>(ctx->i8Slices);
             double *sc = ptr<double>(ctx->i8Scale);
             if (have_i8) CU(ctx, cudaStreamWaitEvent(ctx->s_panel, eI8, 0));  // the slices and the tiles of the previous pass
-            if (i8_split_tiles(tiles, nt, blk_end, c0, I8_BLOCK, i8S, sl, sc, ctx->s_panel)) return fail(ctx, GPL_ERR_CUDA, "i8_split_tiles launch failed");
+            if (i8_split_tiles(tiles, nt, blk_end, c0, i8_block, i8S, sl, sc, ctx->s_panel)) return fail(ctx, GPL_ERR_CUDA, "i8_split_tiles launch failed");
             CU(ctx, cudaEventRecord(eSplit, ctx->s_panel));
-            int irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, 0, cb_a, sms - 1, dinfo, i8dbg, ctx->s_panel);
+            int irc = i8_trail(tiles, nt, blk_end, i8_block, i8S, sl, sc, 0, cb_a, sms - 1, dinfo, i8dbg, ctx->s_panel);
             CU(ctx, cudaStreamWaitEvent(ctx->s_trail, eSplit, 0));
             if (!irc && cb_a < cb_b) {
-                irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, cb_a, cb_b, i8_ctas, dinfo, i8dbg, ctx->s_trail);
+                irc = i8_trail(tiles, nt, blk_end, i8_block, i8S, sl, sc, cb_a, cb_b, i8_ctas, dinfo, i8dbg, ctx->s_trail);
                 ctx->launches++;
             }
             CU(ctx, cudaEventRecord(eB[P], ctx->s_trail));
             if (!irc && cb_b < ncb) {
                 CU(ctx, cudaStreamWaitEvent(ctx->s_i8, eB[P], 0));  // one persistent INT8 kernel at a time next to the chain
-                irc = i8_trail(tiles, nt, blk_end, I8_BLOCK, i8S, sl, sc, cb_b, ncb, i8_ctas, dinfo, i8dbg, ctx->s_i8);
+                irc = i8_trail(tiles, nt, blk_end, i8_block, i8S, sl, sc, cb_b, ncb, i8_ctas, dinfo, i8dbg, ctx->s_i8);
                 ctx->launches++;
             }
             CU(ctx, cudaEventRecord(eI8, ctx->s_i8));

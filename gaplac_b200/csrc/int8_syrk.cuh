@@ -463,7 +463,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Launch on `stream` with at most max_ctas persistent CTAs (<= 0: one per SM).  slices: S x n_rows x K int8.
+// Launch on `stream` with at most max_ctas persistent CTAs (0: one per SM; negative: -max_ctas output blocks per CTA, i.e.
+// short-lived CTAs that hand their SM back to higher-priority streams often).  slices: S x n_rows x K int8.
 // Returns 0, or a negative code (-1 driver entry point, -2 shape, -4 tensor map, -5 launch).
 struct Runtime {
     EncodeTiledFn encode = nullptr;
@@ -512,6 +513,7 @@ static inline int launch(const int8_t *slices, int S, View vw, int max_ctas, cud
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -4;
     int grid = max_ctas > 0 && max_ctas < sms ? max_ctas : sms;
+    if (max_ctas < 0) grid = (ntiles - max_ctas - 1) / -max_ctas;
     if (ntiles < grid) grid = ntiles;
     const Schedule sch = make_schedule(S);
     if (vw.layout == 0) int8_syrk_kernel<0><<<grid, I8_THREADS, SMEM_BYTES, stream>>>(tmap, sch, vw);
