@@ -190,13 +190,41 @@ def run_configs(ctx, dev, flush, quick: bool = False):
         whole_ms = _events(torch, stream, lambda: ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0), 3)
         n = 8192
         f_ms = float(np.mean(fac))
+
+        def factor_ms(nn, option, reps=3):  # the library's own events around the factorisation, for one option value
+            dd = d if nn == 8192 else W.make_c5(n=nn)
+            ctx.set_option("trail_int8", option)
+            ctx.set_option("profile_events", 1)
+            ts, val = [], None
+            for _ in range(reps + 1):
+                val = ctx.lml_large(prog, dd["X"], dd["y"], dd["theta"], 0.0)
+                ts.append(ctx.last_timing()[0][1])
+            ctx.set_option("profile_events", 0)
+            ctx.set_option("trail_int8", -1)
+            return float(np.mean(ts[1:])), val
+
+        dmma_ms, dmma_val = factor_ms(8192, 0)
         e = {"workload": "C5 SqExp(:x; l=1)+Noise n=8192 single model", "factorisation_ms": f_ms,
              "factorisation_tflops": n ** 3 / 3.0 / (f_ms * 1e-3) * 1e-12,
              "factorisation_frac_fp64_peak": n ** 3 / 3.0 / (f_ms * 1e-3) * 1e-12 / peak,
+             "trailing_updates": "INT8 split path on tcgen05 (option trail_int8 = -1: 8 slices from n = 8192 on); FLOPs are those of the "
+                                 "FP64 factorisation it replaces",
+             "fp64_dmma_only": {"factorisation_ms": dmma_ms, "factorisation_tflops": n ** 3 / 3.0 / (dmma_ms * 1e-3) * 1e-12,
+                                "lml_rel_diff": float(abs(dmma_val[0] - lml) / abs(lml))},
              "cov_build_ms": float(np.mean(cov)), "cov_build_gbs": 8.0 * (n * (n + 64) / 2) / (np.mean(cov) * 1e-3) * 1e-9,
              "whole_call_ms": whole_ms, "info": int(info),
              "timing": "CUDA events inside the library around the build and the factorisation (+ forward solve); whole call by "
                        "events on the stream around the blocking host-buffer call"}
+        if not quick:  # beyond the north_star size: where the trailing updates are most of the work
+            big = {}
+            for nn in (12288, 16384):
+                a_ms, a_val = factor_ms(nn, -1, reps=2)
+                b_ms, b_val = factor_ms(nn, 0, reps=2)
+                big[f"n{nn}"] = {"factorisation_ms": a_ms, "factorisation_tflops": nn ** 3 / 3.0 / (a_ms * 1e-3) * 1e-12,
+                                 "factorisation_frac_fp64_peak": nn ** 3 / 3.0 / (a_ms * 1e-3) * 1e-12 / peak,
+                                 "fp64_dmma_only_ms": b_ms, "lml_rel_diff_vs_fp64_path": float(abs(a_val[0] - b_val[0]) / abs(b_val[0])),
+                                 "info": int(a_val[2])}
+            e["larger_n"] = big
         if not quick:
             import scipy.linalg as sla
             K = O.cov(d["ops"], d["X"], d["theta"], 0.0)

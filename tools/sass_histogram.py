@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Opcode histogram per kernel of libgaplac_b200.so (cuobjdump -sass): the evidence for which hardware paths the kernels
 use - DMMA.8x8x4 (FP64 tensor-core path; tcgen05 has no f64 kind), LDGSTS (cp.async), UBLKCP + SYNCS (1-D TMA bulk copies
-on mbarriers), plus registers / stack / shared memory per kernel (cuobjdump -res-usage).
+on mbarriers), UTCIMMA / UTCBAR / LDTM / UTMALDG (tcgen05.mma.kind::i8, tcgen05.commit, tcgen05.ld, tensor-map TMA loads of the
+INT8 trailing update), plus registers / stack / shared memory per kernel (cuobjdump -res-usage).
 
     python tools/sass_histogram.py > profiles/sass_r02.txt"""
 import collections
@@ -13,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "gaplac_b200", "libgaplac_b200.so")
 KEY = ["DMMA", "DFMA", "DMUL", "DADD", "LDGSTS", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "MUFU", "ATOMS",
-       "ATOMG", "RED", "UTCMMA", "LDTM", "UTMALDG", "HMMA"]
+       "ATOMG", "RED", "UTCIMMA", "UTCBAR", "LDTM", "UTMALDG", "HMMA"]
 
 
 def main():
