@@ -119,3 +119,16 @@ def test_workspace_poisoning_does_not_reach_the_result(own_ctx):
     clean = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
     ctx.set_option("poison_ws", 1)
     assert ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0) == clean
+
+
+def test_look_ahead_without_the_worker_cta(own_ctx):
+    """chol_variant 3 (what every n > 8960 takes: the worker protocol stops at 140 tile rows) with the INT8 passes."""
+    ctx = own_ctx
+    d = W.make_c5(n=4608)
+    prog = ctx.program(d["ops"])
+    ctx.set_option("trail_int8", 0)
+    base = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
+    ctx.set_option("chol_variant", 3)
+    ctx.set_option("trail_int8", 8)
+    got = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
+    assert got[2] == 0 and abs(got[0] - base[0]) < 1e-12 * abs(base[0])

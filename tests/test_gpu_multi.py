@@ -57,12 +57,15 @@ def test_multi_reports_which_part_failed():
         m.close()
 
 
-def test_large_n_path_survives_a_busy_device():
+@pytest.mark.parametrize("trail_int8", [0, 8])
+def test_large_n_path_survives_a_busy_device(trail_int8):
     """The look-ahead factorisation hands work between concurrently resident kernels through flags (bounded waits).  Run
-    it while a second context keeps the GPU saturated with batched evaluations: it must finish, and correctly."""
+    it while a second context keeps the GPU saturated with batched evaluations: it must finish, and correctly - with the
+    DMMA trailing updates and with the persistent INT8 kernels (which need whole SMs) alike."""
     from oracle import c_oracle as CO
     busy = _lib.Context(0)
     big = _lib.Context(0)
+    big.set_option("trail_int8", trail_int8)
     d2 = W.make_c2(n=512, B=1024)
     stop = threading.Event()
 
