@@ -473,6 +473,7 @@ struct Runtime {
 // Driver entry point and SM count once per process; the kernels' shared-memory attribute once per device.  This is also
 // what forces the kernels' module to load: a caller that keeps a spinning persistent kernel resident must call it BEFORE
 // that kernel starts (the lazy loading of a first launch waits for the device).
+template <int LAYOUT>
 static inline Runtime *prepare() {
     static std::mutex mu;
     static Runtime rt;
@@ -488,16 +489,16 @@ static inline Runtime *prepare() {
         rt.encode = (EncodeTiledFn)fn;
     }
     if (!(devices_done >> dev & 1)) {
-        if (cudaFuncSetAttribute(int8_syrk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(int8_syrk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(int8_syrk_kernel<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
             return nullptr;
         devices_done |= 1ull << dev;
     }
     return &rt;
 }
 
+template <int LAYOUT>
 static inline int launch(const int8_t *slices, int S, View vw, int max_ctas, cudaStream_t stream) {
-    Runtime *rt = prepare();
+    Runtime *rt = prepare<LAYOUT>();
     if (!rt) return -1;
     const EncodeTiledFn encode = rt->encode;
     const int sms = rt->sms;
@@ -516,8 +517,8 @@ static inline int launch(const int8_t *slices, int S, View vw, int max_ctas, cud
     if (max_ctas < 0) grid = (ntiles - max_ctas - 1) / -max_ctas;
     if (ntiles < grid) grid = ntiles;
     const Schedule sch = make_schedule(S);
-    if (vw.layout == 0) int8_syrk_kernel<0><<<grid, I8_THREADS, SMEM_BYTES, stream>>>(tmap, sch, vw);
-    else int8_syrk_kernel<1><<<grid, I8_THREADS, SMEM_BYTES, stream>>>(tmap, sch, vw);
+    vw.layout = LAYOUT;
+    int8_syrk_kernel<LAYOUT><<<grid, I8_THREADS, SMEM_BYTES, stream>>>(tmap, sch, vw);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) fprintf(stderr, "int8_syrk launch: %s\n", cudaGetErrorString(err));
     return err == cudaSuccess ? 0 : -5;

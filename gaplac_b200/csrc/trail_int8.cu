@@ -73,7 +73,7 @@ i8_split_tiles_kernel(const double *__restrict__ tiles, int nt, int t0, int c0, 
 int i8_prepare() {
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, i8_split_tiles_kernel) != cudaSuccess) return -1;
-    return gpl_i8::prepare() ? 0 : -1;
+    return gpl_i8::prepare<1>() ? 0 : -1;
 }
 
 size_t i8_slices_bytes(int nt, int t0, int kt, int S) {
@@ -104,7 +104,7 @@ int i8_trail(double *tiles, int nt, int t0, int kt, int S, const signed char *sl
     vw.cb1 = cb1 < vw.n_rows / 128 ? cb1 : vw.n_rows / 128;
     vw.dbg = dbg;
     vw.info = info;
-    return gpl_i8::launch(reinterpret_cast<const int8_t *>(slices), S, vw, max_ctas, st);
+    return gpl_i8::launch<1>(reinterpret_cast<const int8_t *>(slices), S, vw, max_ctas, st);
 }
 
 }  // namespace gpl

@@ -121,7 +121,7 @@ int ozaki_update(int n_rows, int K, int S, void *ws, double *C, long ldc, int mo
     vw.cb0 = 0;
     vw.cb1 = n_rows / BM;
     vw.dbg = g_dbg_dev;
-    return launch((const int8_t *)ws, S, vw, 0, (cudaStream_t)stream);
+    return launch<0>((const int8_t *)ws, S, vw, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"
