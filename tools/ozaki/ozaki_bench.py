@@ -2,8 +2,9 @@
 
     python tools/ozaki/ozaki_bench.py [--quick] [--json out.json]
 
-Microbenchmark only: torch supplies the FP64 yardsticks (cuBLAS DGEMM for the same update, cuSOLVER for the panel
-factorisations of the blocked-Cholesky harness); nothing here is on the product path.
+The kernel is the one the library's large-n factorisation uses (gaplac_b200/csrc/int8_syrk.cuh), here on dense matrices.  torch
+supplies the FP64 yardsticks (cuBLAS DGEMM for the same update, cuSOLVER for the panel factorisations of the blocked-Cholesky
+harness); this harness itself is not on the product path.
 """
 import argparse
 import ctypes
