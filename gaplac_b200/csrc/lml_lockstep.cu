@@ -422,7 +422,10 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
 
     // Operand ring: LK_NS slots of 8 KiB.  Update stage s < Q holds 8 columns of both operands (A = tiles (i, 0..j-1),
     // B = tiles (j, 0..j-1)); the three stages after the last update hold columns 0..47 of L_jj as 16-column chunks for
-    // the triangular solve.  LK_NS - 1 stages are in flight; one barrier per stage.
+    // the triangular solve.  LK_NS - 1 stages are in flight; one barrier per stage.  (Measured and dropped at the end of
+    // round 2: the same ring with cp.async.bulk issued by thread 0 and full / empty mbarriers instead of LDGSTS + block
+    // barriers, as in big_trail_kernel - identical bits, headline step 8.73 -> 8.87 ms: with four CTAs per SM the block
+    // barriers are already hidden, and thread 0's issue work lands on the critical warp.)
     constexpr int RKC = 8, RCH = RKC * TS;
     static_assert(2 * RCH == LCH && LK_NS * LCH == TILE_ELEMS, "ring slots fill S");
     const int Q = (TS / RKC) * j;
