@@ -59,12 +59,14 @@ struct gpl_ctx {
     int ou_separable = 1;                   // 1: sort the observations by the OU column and use the separable form (lockstep lml)
     int trail_int8 = -1;                    // large-n trailing updates: -1 auto (INT8 split path, 8 slices, from n = 8192 on), 0 FP64 DMMA only,
                                             // 5..9: that many slices from n = 4096 on
+    int zero_tile_skip = 1;                 // lockstep factorisation: skip updates with / solves of exactly-zero tiles: 1 when the program
+                                            // can produce them (a Cat factor in every term but the noise), 2 always, 0 never
     int poison_ws = 0;                      // 1: fill the whole workspace with NaN payloads before every call (hygiene tests)
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
     int lk_launches[7] = {0, 0, 0, 0, 0, 0, 0};  // alpha / contraction kernels
     // grow-only device buffers
-    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart, lkPerm, lkXs, lkYs, lkDyS;
+    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart, lkPerm, lkXs, lkYs, lkDyS, lkZero;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
 };
 
@@ -108,7 +110,7 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
 // caller's stream): every call that touches the workspace first makes its stream wait for the previous such call and
 // records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
 inline void all_buffers(gpl_ctx *ctx, std::vector<DevBuf *> &out) {
-    out = {&ctx->i8Slices, &ctx->i8Scale, &ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
+    out = {&ctx->lkZero, &ctx->i8Slices, &ctx->i8Scale, &ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
            &ctx->lkM, &ctx->lkGpart, &ctx->lkPerm, &ctx->lkXs, &ctx->lkYs, &ctx->lkDyS, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
            &ctx->bLml, &ctx->bDtheta, &ctx->bDy, &ctx->bInfo, &ctx->bMisc, &ctx->bK, &ctx->bXs, &ctx->bMean, &ctx->bVar, &ctx->bWsV};
 }
@@ -257,8 +259,10 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     if (Bc > B) Bc = B;
     int rc;
     if ((rc = ensure(ctx, ctx->lkTiles, (size_t)Bc * ntri * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkD, (size_t)Bc * nt * DSIZE * 8)) ||
-        (rc = ensure(ctx, ctx->lkZ, (size_t)Bc * nt * TS * 8)) || (rc = ensure(ctx, ctx->lkAcc, (size_t)Bc * 16)))
+        (rc = ensure(ctx, ctx->lkZ, (size_t)Bc * nt * TS * 8)) || (rc = ensure(ctx, ctx->lkAcc, (size_t)Bc * 16)) ||
+        (rc = ensure(ctx, ctx->lkZero, (size_t)Bc * ntri * sizeof(int))))
         return rc;
+    if (nt > GPL_LK_KLMAX) return fail(ctx, GPL_ERR_LIMIT, "batched path: n = %d exceeds %d", n, GPL_LK_KLMAX * TS);
     if (want_grad && ((rc = ensure(ctx, ctx->lkM, (size_t)Bc * ntri * TILE_BYTES)) || (rc = ensure(ctx, ctx->lkW, (size_t)Bc * nt * TILE_BYTES)) ||
                       (rc = ensure(ctx, ctx->lkAlpha, (size_t)Bc * nt * TS * 8)) ||
                       (rc = ensure(ctx, ctx->lkGpart, (size_t)Bc * ntri * (p > 0 ? p : 1) * 8))))
@@ -309,6 +313,16 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     }
     LkParams prm;
     prm.sep_col = sep_col;
+    // exact zero tiles arise when every term but the noise carries a Cat(...) factor (block-diagonal K on grouped rows);
+    // otherwise the flags are not even read (2 forces them on: short length scales underflow to exact zeros as well)
+    bool cat_everywhere = prog.n_terms > 0;
+    for (int t = 0; t < prog.n_terms; ++t) {
+        if (prog.has_noise >> t & 1) continue;
+        bool has_cat = false;
+        for (int f = prog.term_begin[t]; f < prog.term_begin[t + 1]; ++f) has_cat |= prog.f[f].kind == F_CAT;
+        cat_everywhere &= has_cat;
+    }
+    prm.zflag = (ctx->zero_tile_skip == 2 || (ctx->zero_tile_skip == 1 && cat_everywhere)) ? ptr<int>(ctx->lkZero) : nullptr;
     prm.prog = prog;
     prm.n = n;
     prm.d = d;
@@ -806,6 +820,7 @@ int gpl_set_option(gpl_ctx *ctx, const char *key, int value) {
     else if (!strcmp(key, "lk_ws_limit_mb")) ctx->lk_ws_limit = (size_t)value << 20;
     else if (!strcmp(key, "profile_events")) ctx->profile_events = value;
     else if (!strcmp(key, "poison_ws")) ctx->poison_ws = value;
+    else if (!strcmp(key, "zero_tile_skip")) ctx->zero_tile_skip = value;
     else if (!strcmp(key, "trail_int8")) {
         if (value != 0 && value != -1 && (value < 5 || value > 9)) return fail(ctx, GPL_ERR_ARG, "trail_int8: -1 (auto), 0 (off) or 5..9 slices");
         ctx->trail_int8 = value;

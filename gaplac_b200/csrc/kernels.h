@@ -32,6 +32,7 @@ size_t lml_smem_bytes(bool grad);
 #ifndef GPL_LK_CW
 #define GPL_LK_CW 4  // covariance entries per row and interpretation step in the lockstep kernels (4 or 8)
 #endif
+#define GPL_LK_KLMAX 512  // tile rows the lockstep kernels' column list has room for (n <= 32768)
 #ifndef GPL_LK_ZMAX
 #define GPL_LK_ZMAX 1024  // rows of z staged in shared memory by the diagonal-tile kernel
 #endif
@@ -46,6 +47,8 @@ struct LkParams {
     double *dblk;   // B x nt x DSIZE: block inverses of the diagonal tiles
     double *z;      // B x nt*64: right-hand side / z = L^-1 y
     int sep_col;    // >= 0: X is sorted by this column; its OU leaves (at most two) use the separable form below the diagonal
+    int *zflag;     // B x ntri ints or NULL: 1 = the stored tile (i, j), i > j, of L is exactly zero (block-diagonal covariances:
+                    // Cat(...) * k products on grouped rows); updates with such tiles and their triangular solves are skipped
 };
 // sorting the observations by one input column (the log marginal likelihood does not depend on their order)
 __global__ void lk_sort_perm_kernel(const double *xcol, int n, int npow2, int *perm);           // 1 CTA, bitonic

@@ -38,7 +38,26 @@ struct __align__(16) StepSmem {
     ItemScalars sc;
     double zs[GPL_LK_ZMAX];  // z_k of the earlier tile columns (diag kernel)
     SepCtx sep;              // separable OU factors of the current block (lk_below_kernel, sorted inputs)
+    short kl[GPL_LK_KLMAX];  // tile columns k < j whose tiles are not structurally zero (zero-tile skipping)
+    int nk;
 };
+
+// The earlier tile columns k < j this tile's update has to visit: all of them, or (with zero flags) those where neither
+// operand tile is exactly zero.  Warp 0 fills sm.kl / sm.nk (one flag load per lane, one round trip per 32 columns); a
+// block barrier must follow before they are read.
+__device__ __forceinline__ void build_klist(StepSmem &sm, const int *zf, int i, int j, bool both, int tid) {
+    if (tid >= 32) return;
+    int c = 0;
+    for (int k0 = 0; k0 < j; k0 += 32) {
+        const int k = k0 + tid;
+        bool use = k < j;
+        if (use && zf) use = !(zf[tri_index(i, k)] || (both && zf[tri_index(j, k)]));
+        const unsigned m = __ballot_sync(0xffffffffu, use);
+        if (use) sm.kl[c + __popc(m & ((1u << tid) - 1u))] = (short)k;
+        c += __popc(m);
+    }
+    if (tid == 0) sm.nk = c;
+}
 
 __device__ __forceinline__ const double *item_ptr(const double *base, long long stride, int b) {
     return base + (size_t)b * stride;
@@ -46,6 +65,7 @@ __device__ __forceinline__ const double *item_ptr(const double *base, long long 
 
 }  // namespace
 
+static_assert(sizeof(StepSmem) <= 56 * 1024, "four CTAs of the lockstep kernels per SM");
 size_t lk_step_smem_bytes() { return sizeof(StepSmem); }
 
 // ---- diagonal tile of column j: covariance + update, right-hand side update ----------------------------------------
@@ -94,10 +114,19 @@ __device__ __forceinline__ void diag_tile_phase(const LkParams &prm, StepSmem &s
     // only one operand is staged: a ring of LK_NS slots of 16 columns, LK_NS - 1 stages in flight (one barrier per stage)
     constexpr int DKC = 16, DCH = DKC * TS;
     static_assert(DCH == LCH, "one ring slot per stage");
-    const int Q = (TS / DKC) * j;
+    // stage s = chunk s % 4 of the tile (j, kl[s / 4]): only the tiles of row j that are not exactly zero are visited
+    // (without flags - programs that cannot produce exact zeros - the walk is the plain one: no list, no extra barrier)
+    const int *zf = prm.zflag ? prm.zflag + (size_t)b * ntri : nullptr;
+    int Q = (TS / DKC) * j;
+    if (zf) {
+        build_klist(sm, zf, j, j, false, tid);
+        __syncthreads();
+        Q = (TS / DKC) * sm.nk;
+    }
     const double *srcA = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1) are contiguous
+    auto stage_off = [&](int s) { return zf ? (size_t)(sm.kl[s / (TS / DKC)] * (TS / DKC) + s % (TS / DKC)) : (size_t)s; };
     auto issue = [&](int s) {  // always commits, so that the group count tracks the stage number
-        if (s < Q) block_load_async<DCH * 8>(sm.S + (s % LK_NS) * DCH, srcA + (size_t)s * DCH, tid);
+        if (s < Q) block_load_async<DCH * 8>(sm.S + (s % LK_NS) * DCH, srcA + stage_off(s) * DCH, tid);
         cp_async_commit();
     };
     const bool z_in_smem = j * TS <= GPL_LK_ZMAX;
@@ -133,7 +162,7 @@ __device__ __forceinline__ void diag_tile_phase(const LkParams &prm, StepSmem &s
         default: diag_mma<3, DKC>(acc, a, tm); break;
         }
         {
-            const double *zq = zsrc + q * DKC + yhalf;
+            const double *zq = zsrc + stage_off(q) * DKC + yhalf;
 #pragma unroll
             for (int k = 0; k < DKC / 2; k += 2) {
                 yp0 = fma(a[tidx(yrow, yhalf + k)], zq[k], yp0);
@@ -428,15 +457,18 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
     // barriers are already hidden, and thread 0's issue work lands on the critical warp.)
     constexpr int RKC = 8, RCH = RKC * TS;
     static_assert(2 * RCH == LCH && LK_NS * LCH == TILE_ELEMS, "ring slots fill S");
-    const int Q = (TS / RKC) * j;
+    int *zf = prm.zflag ? prm.zflag + (size_t)b * ntri : nullptr;
+    if (zf) build_klist(sm, zf, i, j, true, tid);  // read after the barrier below ("item scalars")
     const double *srcA = wsL + tri_index(i, 0) * TILE_ELEMS;  // tiles (i, 0..j-1)
     const double *srcB = wsL + tri_index(j, 0) * TILE_ELEMS;  // tiles (j, 0..j-1)
     const double *srcL = wsL + tri_index(j, j) * TILE_ELEMS;
+    int Q = (TS / RKC) * j;  // with flags: reset after the barrier to 8 stages per visited tile column
     auto issue = [&](int s) {  // always commits, so that the group count tracks the stage number
         double *dst = sm.S + (s % LK_NS) * LCH;
         if (s < Q) {
-            block_load_async<RCH * 8>(dst, srcA + (size_t)s * RCH, tid);
-            block_load_async<RCH * 8>(dst + RCH, srcB + (size_t)s * RCH, tid);
+            const size_t so = zf ? (size_t)(sm.kl[s / (TS / RKC)] * (TS / RKC) + s % (TS / RKC)) : (size_t)s;
+            block_load_async<RCH * 8>(dst, srcA + so * RCH, tid);
+            block_load_async<RCH * 8>(dst + RCH, srcB + so * RCH, tid);
         } else if (s < Q + 3) {
             block_load_async<LCH * 8>(dst, srcL + (size_t)(s - Q) * LCH, tid);
         }
@@ -448,7 +480,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         static_assert(DSIZE * 8 % (16 * NTHREADS) == 0, "D in whole 16-byte chunks per thread");
         block_load_async<DSIZE * 8>(sm.D, Dg, tid);
     }
-    __syncthreads();  // item scalars
+    __syncthreads();  // item scalars, k-list
+    if (zf) Q = (TS / RKC) * sm.nk;
     // Inputs sorted by column sep_col (the host sorted them: the likelihood does not depend on the order of the
     // observations): every row of this block lies at or above every column, so the OU leaves on that column factor
     // into row and column parts - one exponential per thread here instead of 32 per leaf in the evaluation below.
@@ -499,25 +532,41 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         const double *a = sm.S + (q % LK_NS) * LCH;
         tile_mma<true>(acc, a, a + RCH, tm, 0, RKC);
     }
+    // An exactly zero T_ij (rows and columns of different groups under a Cat(...) product, and nothing to subtract) stays
+    // zero through the solve: store it, flag it, and leave the three L_jj stages unused.
+    bool zero_tile = false;
+    if (zf) {
+        int nz = 0;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int cc = 0; cc < NCC; ++cc) nz |= (acc[mb][cc] != 0.0);
+        zero_tile = !__syncthreads_or(nz);
+        if (tid == 0) zf[tri_index(i, j)] = zero_tile ? 1 : 0;
+    }
+    if (zero_tile) {
+        cp_async_wait<0>();  // the prefetched L_jj chunks and D
+    } else {
     // L_ij = T_ij L_jj^-T, right-looking over the four 16-column panels; chunk c of L_jj is ring stage Q + c
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        cp_async_wait<LK_NS - 2>();
-        __syncthreads();
-        issue(Q + c + LK_NS - 1);  // nothing left to load: an empty group keeps the count in step
-        const double *l = sm.S + ((Q + c) % LK_NS) * LCH;
-        if (c == 0) {
-            trsm_rl_solve<0>(acc, sm.D, tm);
-            trsm_rl_update<0>(acc, l, tm);
-        } else if (c == 1) {
-            trsm_rl_solve<1>(acc, sm.D, tm);
-            trsm_rl_update<1>(acc, l, tm);
-        } else {
-            trsm_rl_solve<2>(acc, sm.D, tm);
-            trsm_rl_update<2>(acc, l, tm);
+        for (int c = 0; c < 3; ++c) {
+            cp_async_wait<LK_NS - 2>();
+            __syncthreads();
+            issue(Q + c + LK_NS - 1);  // nothing left to load: an empty group keeps the count in step
+            const double *l = sm.S + ((Q + c) % LK_NS) * LCH;
+            if (c == 0) {
+                trsm_rl_solve<0>(acc, sm.D, tm);
+                trsm_rl_update<0>(acc, l, tm);
+            } else if (c == 1) {
+                trsm_rl_solve<1>(acc, sm.D, tm);
+                trsm_rl_update<1>(acc, l, tm);
+            } else {
+                trsm_rl_solve<2>(acc, sm.D, tm);
+                trsm_rl_update<2>(acc, l, tm);
+            }
         }
+        trsm_rl_solve<3>(acc, sm.D, tm);
     }
-    trsm_rl_solve<3>(acc, sm.D, tm);
     acc_to_tile(wsL + tri_index(i, j) * TILE_ELEMS, acc, tm);
     if (i == j + 1) {      // the tile just stored completes row j + 1: its diagonal tile can be formed now
         __syncthreads();   // the stores above are visible to the whole CTA; S is free

@@ -111,6 +111,10 @@ uint64_t gpl_launch_count(gpl_ctx *ctx);
  * "ou_separable" (default 1: batched log-densities with n > 192 whose program has one or two OU leaves on one column of a
  * shared X sort the observations by that column - the likelihood does not depend on their order; dy is returned in the
  * caller's order - and evaluate those leaves in separable form below the diagonal; 0: off; 2: from n > 64 on),
+ * "zero_tile_skip" (default 1: batched factorisations of programs whose every term but the noise carries a Cat factor -
+ * block-diagonal covariances once the rows are grouped, e.g. Cat(:subject) * SqExp(:time) - skip the updates with, and the
+ * triangular solves of, tiles of L that are exactly zero; results keep every bit; 2: flags for every program (short length
+ * scales underflow to exact zeros too); 0: off),
  * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
  * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);

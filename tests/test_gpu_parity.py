@@ -358,3 +358,28 @@ def test_predict_batched_runs_in_passes_beyond_the_workspace_cap(ctx):
     rm, rv = CO.mean_and_var(ALL_KINDS, X, U, alpha, Xs, Th[33])
     assert np.max(np.abs(parts[0][33] - rm)) < PRED_TOL * max(1.0, np.max(np.abs(rm)))
     assert np.max(np.abs(parts[1][33] - rv)) < PRED_TOL * max(1.0, np.max(np.abs(rv)))
+
+
+# ---------------------------------------------------------------------------------------------- structurally zero tiles
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_zero_tile_skipping_keeps_every_bit(shuffle):
+    """Block-diagonal covariances (Cat(:subject) * SqExp(:time) on rows grouped by subject: C3) leave most tiles of L exactly
+    zero; the lockstep kernels skip the updates with them and their triangular solves.  Same bits as the dense walk, with
+    grouped rows (tiles are skipped) and with shuffled rows (nothing to skip), lml and gradient."""
+    d = W.make_c3(features=24)
+    X, Y = d["X"].copy(), d["Y"].copy()
+    if shuffle:
+        perm = np.random.default_rng(0).permutation(X.shape[0])
+        X, Y = X[perm], Y[:, perm]
+    c = _lib.Context(0)
+    try:
+        prog = c.program(d["ops"])
+        on = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        c.set_option("zero_tile_skip", 0)
+        off = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        for a, b in zip(on, off):
+            assert np.array_equal(a, b)
+        ref, _ = CO.lml_batched(d["ops"], X, Y, d["Theta"], 0.0)
+        assert np.max(np.abs(on[0] - ref) / np.abs(ref)) < LML_RTOL
+    finally:
+        c.close()
