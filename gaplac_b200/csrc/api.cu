@@ -66,7 +66,7 @@ struct gpl_ctx {
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
     int lk_launches[7] = {0, 0, 0, 0, 0, 0, 0};  // alpha / contraction kernels
     // grow-only device buffers
-    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart, lkPerm, lkXs, lkYs, lkDyS, lkZero;
+    DevBuf lkTiles, lkD, lkZ, lkAcc, lkM, lkGpart, lkPerm, lkXs, lkYs, lkDyS, lkZero, lkMzero;
     DevBuf ws, vec, counter, bX, bY, bTheta, bSigma, bLml, bDtheta, bDy, bInfo, bMisc, bK, bXs, bMean, bVar, bWsV;
 };
 
@@ -110,7 +110,7 @@ int fail(gpl_ctx *ctx, int code, const char *fmt, ...) {
 // caller's stream): every call that touches the workspace first makes its stream wait for the previous such call and
 // records its own completion when it has enqueued everything, so that workspace reuse is ordered across streams.
 inline void all_buffers(gpl_ctx *ctx, std::vector<DevBuf *> &out) {
-    out = {&ctx->lkZero, &ctx->i8Slices, &ctx->i8Scale, &ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
+    out = {&ctx->lkZero, &ctx->lkMzero, &ctx->i8Slices, &ctx->i8Scale, &ctx->bigFlags, &ctx->bigD, &ctx->lkW, &ctx->lkAlpha, &ctx->dStage, &ctx->lkTiles, &ctx->lkD, &ctx->lkZ, &ctx->lkAcc,
            &ctx->lkM, &ctx->lkGpart, &ctx->lkPerm, &ctx->lkXs, &ctx->lkYs, &ctx->lkDyS, &ctx->ws, &ctx->vec, &ctx->counter, &ctx->bX, &ctx->bY, &ctx->bTheta, &ctx->bSigma,
            &ctx->bLml, &ctx->bDtheta, &ctx->bDy, &ctx->bInfo, &ctx->bMisc, &ctx->bK, &ctx->bXs, &ctx->bMean, &ctx->bVar, &ctx->bWsV};
 }
@@ -360,6 +360,13 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     gp.alpha = ptr<double>(ctx->lkAlpha);
     gp.gpart = ptr<double>(ctx->lkGpart);
     gp.sep_col = sep_col;
+    gp.zflag = prm.zflag;
+    gp.mflag = nullptr;
+    if (want_grad && prm.zflag) {
+        if ((rc = ensure(ctx, ctx->lkMzero, (size_t)Bc * ntri * sizeof(int)))) return rc;
+        gp.mflag = ptr<int>(ctx->lkMzero);
+        gp.zflag = ptr<int>(ctx->lkZero);  // (ensure may have moved nothing: same buffer as prm.zflag)
+    }
     auto mark = [&](int kind) {  // kind: 0 diag, 1 potrf, 2 below, 3..6 gradient phases (winv, minv, alpha, contraction), -1 start
         if (!ctx->profile_events) return;
         cudaEvent_t e;

@@ -88,6 +88,8 @@ struct LkGradParams {
     const int *info;
     int B;
     int sep_col;  // >= 0: X is sorted by this column (see LkParams): separable OU factors in the contraction below the diagonal
+    const int *zflag;  // B x ntri or NULL: exactly-zero tiles of L (LkParams::zflag)
+    int *mflag;        // B x ntri or NULL: exactly-zero tiles of M = L^-1 below the diagonal, written by lk_minv_kernel
 };
 __global__ void lk_winv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * nt
 __global__ void lk_minv_kernel(const __grid_constant__ LkGradParams prm);     // grid B * i  (row i, tiles j < i)

@@ -42,6 +42,8 @@ struct __align__(16) GradSmem {
     double al[2 * TS];  // alpha_i | alpha_j
     double gsum[NWARPS * GPL_MAX_THETA];
     SepCtx sep;
+    short kl[GPL_LK_KLMAX];  // tile rows k >= i whose M tiles are not exactly zero (zero-tile skipping)
+    int nk;
 };
 
 // the first tile of a run is triangular: (M_jj)'(row, kk) = 0 for kk < row, so a warp whose rows start at r0 skips the
@@ -89,12 +91,26 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
     const double *srcA = M + col_index(nt, j, j) * TILE_ELEMS;  // (M_kj)', k = j .. i-1
     const double *srcB = L + tri_index(i, j) * TILE_ELEMS;      // L_ik,    k = j .. i-1
     const double *srcW = prm.winv + ((size_t)b * nt + i) * TILE_ELEMS;
-    const int Q = (TS / GKC) * (i - j);
+    // Zero-tile skipping (block-diagonal covariances): the run k = j .. i-1 shrinks to the k where neither (M_kj)' nor L_ik
+    // is exactly zero; a tile of M that comes out exactly zero is flagged for the phases that read M.
+    __shared__ short kl[GPL_LK_KLMAX];
+    __shared__ int nk;
+    const int *zf = prm.zflag ? prm.zflag + (size_t)b * ntri : nullptr;
+    int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
+    int Q = (TS / GKC) * (i - j);
+    bool tri_first = true;  // the first stages belong to the triangular (M_jj)'
+    if (zf) {
+        build_tile_list(kl, &nk, j, i, [&](int k) { return !(zf[tri_index(i, k)] || (k > j && mf[tri_index(k, j)])); }, tid);
+        __syncthreads();
+        Q = (TS / GKC) * nk;
+        tri_first = nk > 0 && kl[0] == j;
+    }
     auto issue = [&](int s) {  // always commits: the group count tracks the stage number
         double *dst = S + (s % GNS) * GSLOT;
         if (s < Q) {
-            block_load_async<GCH * 8>(dst, srcA + (size_t)s * GCH, tid);
-            block_load_async<GCH * 8>(dst + GCH, srcB + (size_t)s * GCH, tid);
+            const size_t so = zf ? (size_t)((kl[s / (TS / GKC)] - j) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
+            block_load_async<GCH * 8>(dst, srcA + so * GCH, tid);
+            block_load_async<GCH * 8>(dst + GCH, srcB + so * GCH, tid);
         } else if (s < Q + GNS) {  // W_ii in 16-column chunks: Q is a multiple of GNS, so the ring becomes the whole tile
             block_load_async<GSLOT * 8>(dst, srcW + (size_t)(s - Q) * GSLOT, tid);
         }
@@ -109,13 +125,24 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
         __syncthreads();
         issue(q + GNS - 1);
         const double *a = S + (q % GNS) * GSLOT;
-        if (!stage_is_zero(q, tm)) tile_mma<true>(acc, a, a + GCH, tm, 0, GKC);
+        if (!(tri_first && stage_is_zero(q, tm))) tile_mma<true>(acc, a, a + GCH, tm, 0, GKC);
     }
     __syncthreads();  // the slot of the last update stage is free
     issue(Q + GNS - 1);
     cp_async_wait<0>();
-    __syncthreads();
-    tile_trsm_w(acc, S, tm);  // (M_ij)' = acc W_ii'
+    bool zero_tile = false;
+    if (mf) {
+        int nz = 0;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int cc = 0; cc < NCC; ++cc) nz |= (acc[mb][cc] != 0.0);
+        zero_tile = !__syncthreads_or(nz);
+        if (tid == 0) mf[tri_index(i, j)] = zero_tile ? 1 : 0;
+    } else {
+        __syncthreads();
+    }
+    if (!zero_tile) tile_trsm_w(acc, S, tm);  // (M_ij)' = acc W_ii'
     acc_to_tile(M + col_index(nt, i, j) * TILE_ELEMS, acc, tm);
 }
 
@@ -129,7 +156,9 @@ __global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constan
     const double *z = prm.z + (size_t)b * nt * TS;
     const int row = tid & (TS - 1), half = tid >> 6;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
     for (int k = j; k < nt; ++k) {
+        if (mf && k > j && mf[tri_index(k, j)]) continue;  // an exactly-zero (M_kj)' adds nothing
         const double *T = run + (size_t)(k - j) * TILE_ELEMS;
         const double *zk = z + k * TS + 32 * half;
 #pragma unroll 4
@@ -176,12 +205,23 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
     const bool same = (i == j);
     const double *srcA = M + col_index(nt, i, i) * TILE_ELEMS;  // (M_ki)', k = i .. nt-1
     const double *srcB = M + col_index(nt, i, j) * TILE_ELEMS;  // (M_kj)', k = i .. nt-1
-    const int Q = (TS / GKC) * (nt - i);
+    // zero-tile skipping: the run k = i .. nt-1 shrinks to the k where neither (M_ki)' nor (M_kj)' is exactly zero
+    const int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
+    int Q = (TS / GKC) * (nt - i);
+    bool tri_first = true, last_is_ragged = true;
+    if (mf) {
+        build_tile_list(sm.kl, &sm.nk, i, nt, [&](int k) { return !((k > i && mf[tri_index(k, i)]) || (k > j && mf[tri_index(k, j)])); }, tid);
+        __syncthreads();
+        Q = (TS / GKC) * sm.nk;
+        tri_first = sm.nk > 0 && sm.kl[0] == i;
+        last_is_ragged = sm.nk > 0 && sm.kl[sm.nk - 1] == nt - 1;
+    }
     auto issue = [&](int s) {
         double *dst = sm.S + (s % GNS) * GSLOT;
         if (s < Q) {
-            block_load_async<GCH * 8>(dst, srcA + (size_t)s * GCH, tid);
-            if (!same) block_load_async<GCH * 8>(dst + GCH, srcB + (size_t)s * GCH, tid);
+            const size_t so = mf ? (size_t)((sm.kl[s / (TS / GKC)] - i) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
+            block_load_async<GCH * 8>(dst, srcA + so * GCH, tid);
+            if (!same) block_load_async<GCH * 8>(dst + GCH, srcB + so * GCH, tid);
         }
         cp_async_commit();
     };
@@ -192,13 +232,13 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
     // Ragged n: the last tile row of M ends in identity padding; in every (M_ki)' with k = nt - 1 the columns kk >= vlast
     // are zero (or the padding identity, which only reaches entries outside the matrix): those stages are skipped.
     const int vlast = n - (nt - 1) * TS;                                  // valid rows of the last tile (1 .. 64)
-    const int q_dead = Q - (TS / GKC) + (vlast + GKC - 1) / GKC;          // first stage of the last tile that is all padding
+    const int q_dead = last_is_ragged ? Q - (TS / GKC) + (vlast + GKC - 1) / GKC : Q;  // first stage of the last tile that is all padding
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<GNS - 2>();
         __syncthreads();
         issue(q + GNS - 1);
         const double *a = sm.S + (q % GNS) * GSLOT;
-        if (stage_is_zero(q, tm) || q >= q_dead) continue;
+        if ((tri_first && stage_is_zero(q, tm)) || q >= q_dead) continue;
         // a diagonal tile of K^-1 is symmetric: warp w (rows 16w ..) only needs the columns up to its own diagonal block
         if (same) tile_mma<false, 0xFF, true>(acc, a, a, tm, 0, GKC, 2 * warp + 2);
         else tile_mma<false>(acc, a, a + GCH, tm, 0, GKC);

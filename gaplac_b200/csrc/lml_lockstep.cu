@@ -43,20 +43,9 @@ struct __align__(16) StepSmem {
 };
 
 // The earlier tile columns k < j this tile's update has to visit: all of them, or (with zero flags) those where neither
-// operand tile is exactly zero.  Warp 0 fills sm.kl / sm.nk (one flag load per lane, one round trip per 32 columns); a
-// block barrier must follow before they are read.
+// operand tile is exactly zero.  Warp 0 fills sm.kl / sm.nk (build_tile_list); a block barrier must follow.
 __device__ __forceinline__ void build_klist(StepSmem &sm, const int *zf, int i, int j, bool both, int tid) {
-    if (tid >= 32) return;
-    int c = 0;
-    for (int k0 = 0; k0 < j; k0 += 32) {
-        const int k = k0 + tid;
-        bool use = k < j;
-        if (use && zf) use = !(zf[tri_index(i, k)] || (both && zf[tri_index(j, k)]));
-        const unsigned m = __ballot_sync(0xffffffffu, use);
-        if (use) sm.kl[c + __popc(m & ((1u << tid) - 1u))] = (short)k;
-        c += __popc(m);
-    }
-    if (tid == 0) sm.nk = c;
+    build_tile_list(sm.kl, &sm.nk, 0, j, [&](int k) { return !(zf && (zf[tri_index(i, k)] || (both && zf[tri_index(j, k)]))); }, tid);
 }
 
 __device__ __forceinline__ const double *item_ptr(const double *base, long long stride, int b) {

@@ -521,6 +521,22 @@ __device__ __forceinline__ double tile_row_dot(const double *T, const double *v,
     return s;
 }
 
+// Compacted list of the tile indices k in [k0, k1) for which use_k(k) holds, built by warp 0 (one predicate evaluation per
+// lane, one ballot per 32 indices); *nk receives the count.  A block barrier must follow before kl / nk are read.
+template <class Pred>
+__device__ __forceinline__ void build_tile_list(short *kl, int *nk, int k0, int k1, Pred use_k, int tid) {
+    if (tid >= 32) return;
+    int c = 0;
+    for (int kb = k0; kb < k1; kb += 32) {
+        const int k = kb + tid;
+        const bool use = k < k1 && use_k(k);
+        const unsigned m = __ballot_sync(0xffffffffu, use);
+        if (use) kl[c + __popc(m & ((1u << tid) - 1u))] = (short)k;
+        c += __popc(m);
+    }
+    if (tid == 0) *nk = c;
+}
+
 // deterministic block-wide sum, result valid in every thread; red = NWARPS doubles of shared memory
 __device__ __forceinline__ double block_sum(double v, double *red, int tid) {
 #pragma unroll
