@@ -250,6 +250,8 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
         CU(ctx, cudaFuncSetAttribute(lk_winv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_winv_smem_bytes()));
         CU(ctx, cudaFuncSetAttribute(lk_minv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
         CU(ctx, cudaFuncSetAttribute(lk_gradc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_grad_smem_bytes()));
+        CU(ctx, cudaFuncSetAttribute(lk_minv_skip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+        CU(ctx, cudaFuncSetAttribute(lk_gradc_skip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lk_grad_smem_bytes()));
         ctx->attr_lk = true;
     }
     const size_t grad_item = want_grad ? (size_t)(ntri + nt) * TILE_BYTES + (size_t)nt * TS * 8 + (size_t)ntri * (p > 0 ? p : 1) * 8 : 0;
@@ -420,15 +422,18 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
             mark(3);
             for (int i = 1; i < nt; ++i) {
                 gp.i = i;
-                lk_minv_kernel<<<(unsigned)((size_t)nb * i), NTHREADS, TILE_BYTES, st>>>(gp);
+                if (gp.mflag) lk_minv_skip_kernel<<<(unsigned)((size_t)nb * i), NTHREADS, TILE_BYTES, st>>>(gp);
+                else lk_minv_kernel<<<(unsigned)((size_t)nb * i), NTHREADS, TILE_BYTES, st>>>(gp);
                 ctx->launches++;
                 mark(4);
             }
-            lk_alpha_kernel<<<(unsigned)((size_t)nb * nt), NTHREADS, 0, st>>>(gp);
+            if (gp.mflag) lk_alpha_skip_kernel<<<(unsigned)((size_t)nb * nt), NTHREADS, 0, st>>>(gp);
+            else lk_alpha_kernel<<<(unsigned)((size_t)nb * nt), NTHREADS, 0, st>>>(gp);
             ctx->launches++;
             mark(5);
             if (p > 0 && ddtheta) {
-                lk_gradc_kernel<<<(unsigned)((size_t)nb * ntri), NTHREADS, lk_grad_smem_bytes(), st>>>(gp);
+                if (gp.mflag) lk_gradc_skip_kernel<<<(unsigned)((size_t)nb * ntri), NTHREADS, lk_grad_smem_bytes(), st>>>(gp);
+                else lk_gradc_kernel<<<(unsigned)((size_t)nb * ntri), NTHREADS, lk_grad_smem_bytes(), st>>>(gp);
                 lk_gradsum_kernel<<<(nb + 127) / 128, 128, 0, st>>>(gp);
                 ctx->launches += 2;
                 mark(6);

@@ -96,6 +96,10 @@ __global__ void lk_minv_kernel(const __grid_constant__ LkGradParams prm);     //
 __global__ void lk_alpha_kernel(const __grid_constant__ LkGradParams prm);    // grid B * nt
 __global__ void lk_gradc_kernel(const __grid_constant__ LkGradParams prm);    // grid B * ntri
 __global__ void lk_gradsum_kernel(const __grid_constant__ LkGradParams prm);  // grid ceil(B / 128)
+// the same three phases with zero-tile skipping (zflag / mflag set): separate instantiations, the dense ones stay as they were
+__global__ void lk_minv_skip_kernel(const __grid_constant__ LkGradParams prm);
+__global__ void lk_alpha_skip_kernel(const __grid_constant__ LkGradParams prm);
+__global__ void lk_gradc_skip_kernel(const __grid_constant__ LkGradParams prm);
 size_t lk_winv_smem_bytes();
 size_t lk_grad_smem_bytes();
 

@@ -67,6 +67,41 @@ __device__ __forceinline__ void prepare_item_scalars(const DevProgram &P, const 
     }
 }
 
+// True (block-uniform) iff the 64 x 64 tile (rows ti*64.., columns tj*64.. of the same observation set X) is zero for every
+// hyperparameter value: every term but the noise has a Cat factor none of whose row categories occurs among the columns
+// (rows / columns of different subjects under Cat(:subject) * k).  K and dK/dtheta vanish on such a tile, so its
+// covariance code can be skipped outright.  Guarded so that skipping cannot hide a non-finite value (0 * NaN): all item
+// scalars and the tile's inputs must be finite.  scratch: 64 doubles of shared memory; contains block barriers.
+__device__ __forceinline__ bool tile_cat_dead(const DevProgram &P, const ItemScalars &S, const double *__restrict__ X, int n, int d,
+                                              int ti, int tj, double *scratch, int tid) {
+    const int loc = tid & 63, idx = (tid < 64 ? ti : tj) * 64 + loc;
+    int bad = 0;
+    if (tid < 128 && idx < n)
+        for (int c = 0; c < d; ++c) bad |= !isfinite(X[(size_t)c * n + idx]);
+    if (tid < P.n_factors) bad |= !isfinite(S.a[tid]) | !isfinite(S.da[tid]);
+    if (tid < P.n_terms) bad |= !isfinite(S.tc[tid]);
+    if (__syncthreads_or(bad)) return false;
+    for (int t = 0; t < P.n_terms; ++t) {
+        if (P.has_noise >> t & 1) continue;
+        bool term_dead = false;
+        for (int f = P.leaf_begin[t]; f < P.term_begin[t + 1] && !term_dead; ++f) {
+            if (P.f[f].kind != F_CAT) continue;
+            const double *xc = X + (size_t)P.f[f].col * n;
+            if (tid < 64) scratch[tid] = (tj * 64 + tid < n) ? xc[tj * 64 + tid] : NAN;  // padding columns match nothing
+            __syncthreads();
+            int match = 0;
+            if (tid < 64 && ti * 64 + tid < n) {
+                const double xi = xc[ti * 64 + tid];
+#pragma unroll 8
+                for (int c = 0; c < 64; ++c) match |= (xi == scratch[c]);
+            }
+            term_dead = !__syncthreads_or(match);
+        }
+        if (!term_dead) return false;
+    }
+    return P.n_terms > 0;
+}
+
 // Evaluate the program on the block rows gi[0..R) x cols gj[0..C).
 //   Xa: column-major, leading dimension lda, na valid rows (row indices); Xb likewise for column indices.
 //   SAME: Xa and Xb are the same observation set (K(X,X)): Noise = [gi == gj], diag_add goes on gi == gj,

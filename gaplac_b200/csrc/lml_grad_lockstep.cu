@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_winv_kernel(const __grid_const
 }
 
 // ---- row i of M = L^-1 (tiles j < i) -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_constant__ LkGradParams prm) {
+template <bool SKIP>
+__device__ __forceinline__ void lk_minv_body(const LkGradParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *S = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x, nt = prm.nt, i = prm.i;
@@ -93,13 +94,13 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
     const double *srcW = prm.winv + ((size_t)b * nt + i) * TILE_ELEMS;
     // Zero-tile skipping (block-diagonal covariances): the run k = j .. i-1 shrinks to the k where neither (M_kj)' nor L_ik
     // is exactly zero; a tile of M that comes out exactly zero is flagged for the phases that read M.
-    __shared__ short kl[GPL_LK_KLMAX];
+    __shared__ short kl[SKIP ? GPL_LK_KLMAX : 1];
     __shared__ int nk;
-    const int *zf = prm.zflag ? prm.zflag + (size_t)b * ntri : nullptr;
-    int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
+    const int *zf = SKIP ? prm.zflag + (size_t)b * ntri : nullptr;
+    int *mf = SKIP ? prm.mflag + (size_t)b * ntri : nullptr;
     int Q = (TS / GKC) * (i - j);
     bool tri_first = true;  // the first stages belong to the triangular (M_jj)'
-    if (zf) {
+    if (SKIP) {
         build_tile_list(kl, &nk, j, i, [&](int k) { return !(zf[tri_index(i, k)] || (k > j && mf[tri_index(k, j)])); }, tid);
         __syncthreads();
         Q = (TS / GKC) * nk;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
     auto issue = [&](int s) {  // always commits: the group count tracks the stage number
         double *dst = S + (s % GNS) * GSLOT;
         if (s < Q) {
-            const size_t so = zf ? (size_t)((kl[s / (TS / GKC)] - j) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
+            const size_t so = SKIP ? (size_t)((kl[s / (TS / GKC)] - j) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
             block_load_async<GCH * 8>(dst, srcA + so * GCH, tid);
             block_load_async<GCH * 8>(dst + GCH, srcB + so * GCH, tid);
         } else if (s < Q + GNS) {  // W_ii in 16-column chunks: Q is a multiple of GNS, so the ring becomes the whole tile
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
     issue(Q + GNS - 1);
     cp_async_wait<0>();
     bool zero_tile = false;
-    if (mf) {
+    if (SKIP) {
         int nz = 0;
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
@@ -145,9 +146,12 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_const
     if (!zero_tile) tile_trsm_w(acc, S, tm);  // (M_ij)' = acc W_ii'
     acc_to_tile(M + col_index(nt, i, j) * TILE_ELEMS, acc, tm);
 }
+__global__ void __launch_bounds__(NTHREADS, 4) lk_minv_kernel(const __grid_constant__ LkGradParams prm) { lk_minv_body<false>(prm); }
+__global__ void __launch_bounds__(NTHREADS, 4) lk_minv_skip_kernel(const __grid_constant__ LkGradParams prm) { lk_minv_body<true>(prm); }
 
 // ---- alpha = M' z --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constant__ LkGradParams prm) {
+template <bool SKIP>
+__device__ __forceinline__ void lk_alpha_body(const LkGradParams &prm) {
     __shared__ double part[TS];
     const int tid = threadIdx.x, nt = prm.nt;
     const int b = blockIdx.x / nt, j = blockIdx.x - b * nt;
@@ -156,9 +160,9 @@ __global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constan
     const double *z = prm.z + (size_t)b * nt * TS;
     const int row = tid & (TS - 1), half = tid >> 6;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
+    const int *mf = SKIP ? prm.mflag + (size_t)b * ntri : nullptr;
     for (int k = j; k < nt; ++k) {
-        if (mf && k > j && mf[tri_index(k, j)]) continue;  // an exactly-zero (M_kj)' adds nothing
+        if (SKIP && k > j && mf[tri_index(k, j)]) continue;  // an exactly-zero (M_kj)' adds nothing
         const double *T = run + (size_t)(k - j) * TILE_ELEMS;
         const double *zk = z + k * TS + 32 * half;
 #pragma unroll 4
@@ -180,12 +184,15 @@ __global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constan
         if (prm.dy && g < prm.n) prm.dy[(size_t)b * prm.n + g] = prm.info[b] ? NAN : -a;
     }
 }
+__global__ void __launch_bounds__(NTHREADS) lk_alpha_kernel(const __grid_constant__ LkGradParams prm) { lk_alpha_body<false>(prm); }
+__global__ void __launch_bounds__(NTHREADS) lk_alpha_skip_kernel(const __grid_constant__ LkGradParams prm) { lk_alpha_body<true>(prm); }
 
 // ---- tiles of K^-1 contracted with dK/dtheta --------------------------------------------------------------------------------
 #ifndef GPL_GRADC_CTAS
 #define GPL_GRADC_CTAS 4  // 126 registers, no spills: four CTAs per SM like the other streaming kernels (150 registers at three)
 #endif
-__global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(const __grid_constant__ LkGradParams prm) {
+template <bool SKIP>
+__device__ __forceinline__ void lk_gradc_body(const LkGradParams &prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GradSmem &sm = *reinterpret_cast<GradSmem *>(smem_raw);
     const DevProgram &P = prm.prog;
@@ -203,13 +210,20 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
     else sm.al[tid] = prm.alpha[(size_t)b * nt * TS + j * TS + tid - TS];
     if (tid < NWARPS * GPL_MAX_THETA) sm.gsum[tid] = 0.0;
     const bool same = (i == j);
+    if (SKIP && !same) {  // programs with structural zeros only (see LkParams::zflag)
+        __syncthreads();       // item scalars
+        if (tile_cat_dead(P, sm.sc, X, n, prm.d, i, j, sm.S, tid)) {  // dK/dtheta vanishes on the tile: nothing to contract
+            if (tid < prm.p) prm.gpart[((size_t)b * ntri + t) * prm.p + tid] = 0.0;
+            return;
+        }
+    }
     const double *srcA = M + col_index(nt, i, i) * TILE_ELEMS;  // (M_ki)', k = i .. nt-1
     const double *srcB = M + col_index(nt, i, j) * TILE_ELEMS;  // (M_kj)', k = i .. nt-1
     // zero-tile skipping: the run k = i .. nt-1 shrinks to the k where neither (M_ki)' nor (M_kj)' is exactly zero
-    const int *mf = prm.mflag ? prm.mflag + (size_t)b * ntri : nullptr;
+    const int *mf = SKIP ? prm.mflag + (size_t)b * ntri : nullptr;
     int Q = (TS / GKC) * (nt - i);
     bool tri_first = true, last_is_ragged = true;
-    if (mf) {
+    if (SKIP) {
         build_tile_list(sm.kl, &sm.nk, i, nt, [&](int k) { return !((k > i && mf[tri_index(k, i)]) || (k > j && mf[tri_index(k, j)])); }, tid);
         __syncthreads();
         Q = (TS / GKC) * sm.nk;
@@ -219,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
     auto issue = [&](int s) {
         double *dst = sm.S + (s % GNS) * GSLOT;
         if (s < Q) {
-            const size_t so = mf ? (size_t)((sm.kl[s / (TS / GKC)] - i) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
+            const size_t so = SKIP ? (size_t)((sm.kl[s / (TS / GKC)] - i) * (TS / GKC) + s % (TS / GKC)) : (size_t)s;
             block_load_async<GCH * 8>(dst, srcA + so * GCH, tid);
             if (!same) block_load_async<GCH * 8>(dst + GCH, srcB + so * GCH, tid);
         }
@@ -293,6 +307,8 @@ __global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(cons
         prm.gpart[((size_t)b * ntri + t) * prm.p + tid] = g;
     }
 }
+__global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_kernel(const __grid_constant__ LkGradParams prm) { lk_gradc_body<false>(prm); }
+__global__ void __launch_bounds__(NTHREADS, GPL_GRADC_CTAS) lk_gradc_skip_kernel(const __grid_constant__ LkGradParams prm) { lk_gradc_body<true>(prm); }
 
 __global__ void __launch_bounds__(128) lk_gradsum_kernel(const __grid_constant__ LkGradParams prm) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(NTHREADS, 4) lk_below_kernel(const __grid_cons
         // i > j: no entry of this tile is on the diagonal, so the cross-covariance form applies (Noise terms and the
         // diagonal bookkeeping drop out; rows / columns >= n read as 0 either way)
         double *const slot[4] = {sm.S, sm.S + LCH, sm.S + 2 * LCH, sm.S + 3 * LCH};
-        eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc, 4, sep);
+        // rows and columns that share no category under the program's Cat factors: the tile of K is zero whatever theta is
+        if (zf && tile_cat_dead(P, sm.sc, X, n, prm.d, i, j, sm.S, tid)) acc_zero(acc);
+        else eval_block_acc_scr<false, 4, GPL_LK_CW>(P, sm.sc, X, n, n, gi, X, n, n, j * TS, tm.t, 0.0, slot, tid, acc, 4, sep);
         __syncthreads();  // quarters read back: S is free for the ring
     }
 #pragma unroll

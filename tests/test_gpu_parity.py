@@ -374,12 +374,23 @@ def test_zero_tile_skipping_keeps_every_bit(shuffle):
     c = _lib.Context(0)
     try:
         prog = c.program(d["ops"])
-        on = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        Theta = d["Theta"].copy()
+        Theta[3, 0] = -1.0   # a poisoned length scale: that item is NaN / not positive definite either way
+        Theta[5, 1] = 0.0    # no noise: K is singular for tied categories or fine otherwise - same answer either way
+        on = c.lml_batched(prog, X, Y, Theta, 0.0, grad=True)
         c.set_option("zero_tile_skip", 0)
-        off = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        off = c.lml_batched(prog, X, Y, Theta, 0.0, grad=True)
         for a, b in zip(on, off):
-            assert np.array_equal(a, b)
-        ref, _ = CO.lml_batched(d["ops"], X, Y, d["Theta"], 0.0)
-        assert np.max(np.abs(on[0] - ref) / np.abs(ref)) < LML_RTOL
+            assert np.array_equal(a, b, equal_nan=True)
+        good = np.ones(len(Theta), bool)
+        good[[3, 5]] = False
+        ref, _ = CO.lml_batched(d["ops"], X, Y[good], Theta[good], 0.0)
+        assert np.max(np.abs(on[0][good] - ref) / np.abs(ref)) < LML_RTOL
+        # the posterior path (keeps the factor) walks the same kernels
+        c.set_option("zero_tile_skip", 1)
+        m1, v1, l1, i1 = c.predict_batched(prog, X, Y[0], Theta[:3], 0.0, X[:40] + 0.25)
+        c.set_option("zero_tile_skip", 0)
+        m0, v0, l0, i0 = c.predict_batched(prog, X, Y[0], Theta[:3], 0.0, X[:40] + 0.25)
+        assert np.array_equal(m1, m0) and np.array_equal(v1, v0) and np.array_equal(l1, l0)
     finally:
         c.close()
