@@ -60,7 +60,8 @@ struct gpl_ctx {
     int trail_int8 = -1;                    // large-n trailing updates: -1 auto (INT8 split path, 8 slices, from n = 8192 on), 0 FP64 DMMA only,
                                             // 5..9: that many slices from n = 4096 on
     int zero_tile_skip = 1;                 // lockstep factorisation: skip updates with / solves of exactly-zero tiles: 1 when the program
-                                            // can produce them (a Cat factor in every term but the noise), 2 always, 0 never
+                                            // can produce them (a Cat factor in every term but the noise), 2 always, 0 never,
+                                            // 3: as 1, and group the observations by the shared category column first
     int poison_ws = 0;                      // 1: fill the whole workspace with NaN payloads before every call (hygiene tests)
     int profile_events = 0;                 // 1: time every lockstep launch with CUDA events (bench.py roofline pass)
     double lk_ms[7] = {0, 0, 0, 0, 0, 0, 0};  // last instrumented call: total ms in diag / potrf / below / winv / minv /
@@ -281,8 +282,40 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     // entry instead of an exponential (kfun.cuh SepCtx).  The decision depends on the model alone (n, the program), never on
     // the batch: an item's bits must not depend on how many items travel with it (parts of a multi-device call, the
     // shrinking batch of the sampler).  From four tile columns on the three small launches of the sort cost < 5 % of a call.
-    int sep_col = -1;
-    if (ctx->ou_separable && allow_sort && !x_batched && n <= 8192 && (nt >= 4 || (ctx->ou_separable == 2 && nt >= 2))) {
+    // Exact zero tiles arise when every term but the noise carries a Cat(...) factor: K is block-diagonal once the rows are
+    // grouped by a category column that all those terms share.  Such programs get the flags of LkParams::zflag; with
+    // zero_tile_skip = 3 their observations are also grouped here (a stable sort by that column; rows that arrive grouped in
+    // ascending category order keep their order and their bits) and the separable OU form is not used (rows of different
+    // groups are not ordered along the OU column).
+    bool cat_everywhere = prog.n_terms > 0;
+    int group_col = -1;
+    {
+        unsigned long long common = ~0ull;  // category columns (< 64) present in every term but the noise
+        int real_terms = 0;
+        for (int t = 0; t < prog.n_terms; ++t) {
+            if (prog.has_noise >> t & 1) continue;
+            ++real_terms;
+            unsigned long long cols = 0;
+            bool has_cat = false;
+            for (int f = prog.term_begin[t]; f < prog.term_begin[t + 1]; ++f)
+                if (prog.f[f].kind == F_CAT) {
+                    has_cat = true;
+                    if (prog.f[f].col < 64) cols |= 1ull << prog.f[f].col;
+                }
+            cat_everywhere &= has_cat;
+            common &= cols;
+        }
+        cat_everywhere &= real_terms > 0;
+        if (cat_everywhere && common)
+            for (int c = 0; c < 64 && group_col < 0; ++c)
+                if (common >> c & 1) group_col = c;
+    }
+    const bool use_zflags = ctx->zero_tile_skip == 2 || (ctx->zero_tile_skip && cat_everywhere);
+    int sep_col = -1, sort_col = -1;
+    // grouping is opt-in (zero_tile_skip = 3): three extra launches and two permutations per call cost the sampler's small
+    // batches 12 % (C3, rows already grouped), so by default the caller's row order is taken as it comes
+    if (ctx->zero_tile_skip == 3 && cat_everywhere && group_col >= 0 && allow_sort && !x_batched && n <= 8192 && nt >= 2) sort_col = group_col;
+    else if (ctx->ou_separable && allow_sort && !x_batched && n <= 8192 && (nt >= 4 || (ctx->ou_separable == 2 && nt >= 2))) {
         int cnt = 0;
         for (int f = 0; f < prog.n_factors; ++f)
             if (prog.f[f].kind == F_OU) {
@@ -290,9 +323,10 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
                 if (prog.f[f].col == sep_col) ++cnt;
             }
         if (cnt < 1 || cnt > 2) sep_col = -1;
+        sort_col = sep_col;
     }
     double *ddy_user = ddy;
-    if (sep_col >= 0) {
+    if (sort_col >= 0) {
         const size_t ny = (size_t)n * (y_batched ? B : 1);
         if ((rc = ensure(ctx, ctx->lkPerm, (size_t)n * 4)) || (rc = ensure(ctx, ctx->lkXs, (size_t)n * d * 8)) ||
             (rc = ensure(ctx, ctx->lkYs, ny * 8)) || (ddy && (rc = ensure(ctx, ctx->lkDyS, (size_t)n * B * 8))))
@@ -305,7 +339,7 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
             ctx->attr_sort = true;
         }
         int *perm = ptr<int>(ctx->lkPerm);
-        lk_sort_perm_kernel<<<1, npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024, sort_smem, st>>>(dX + (size_t)sep_col * n, n, npow2, perm);
+        lk_sort_perm_kernel<<<1, npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024, sort_smem, st>>>(dX + (size_t)sort_col * n, n, npow2, perm);
         lk_permute_kernel<<<64, 256, 0, st>>>(dX, ptr<double>(ctx->lkXs), perm, n, d, 0);
         lk_permute_kernel<<<ny > 65536 ? 592 : 64, 256, 0, st>>>(dY, ptr<double>(ctx->lkYs), perm, n, (long long)(ny / n), 0);
         ctx->launches += 3;
@@ -315,16 +349,7 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     }
     LkParams prm;
     prm.sep_col = sep_col;
-    // exact zero tiles arise when every term but the noise carries a Cat(...) factor (block-diagonal K on grouped rows);
-    // otherwise the flags are not even read (2 forces them on: short length scales underflow to exact zeros as well)
-    bool cat_everywhere = prog.n_terms > 0;
-    for (int t = 0; t < prog.n_terms; ++t) {
-        if (prog.has_noise >> t & 1) continue;
-        bool has_cat = false;
-        for (int f = prog.term_begin[t]; f < prog.term_begin[t + 1]; ++f) has_cat |= prog.f[f].kind == F_CAT;
-        cat_everywhere &= has_cat;
-    }
-    prm.zflag = (ctx->zero_tile_skip == 2 || (ctx->zero_tile_skip == 1 && cat_everywhere)) ? ptr<int>(ctx->lkZero) : nullptr;
+    prm.zflag = use_zflags ? ptr<int>(ctx->lkZero) : nullptr;
     prm.prog = prog;
     prm.n = n;
     prm.d = d;
@@ -440,7 +465,7 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
             }
         }
     }
-    if (sep_col >= 0 && ddy_user) {  // dlml/dy back to the caller's order of the observations
+    if (sort_col >= 0 && ddy_user) {  // dlml/dy back to the caller's order of the observations
         lk_permute_kernel<<<592, 256, 0, st>>>(ddy, ddy_user, ptr<int>(ctx->lkPerm), n, B, 1);
         ctx->launches++;
     }

@@ -114,7 +114,9 @@ uint64_t gpl_launch_count(gpl_ctx *ctx);
  * "zero_tile_skip" (default 1: batched factorisations of programs whose every term but the noise carries a Cat factor -
  * block-diagonal covariances once the rows are grouped, e.g. Cat(:subject) * SqExp(:time) - skip the updates with, and the
  * triangular solves of, tiles of L that are exactly zero; results keep every bit; 2: flags for every program (short length
- * scales underflow to exact zeros too); 0: off),
+ * scales underflow to exact zeros too); 3: as 1, and the observations are first grouped by the category column those terms
+ * share - for rows that do not arrive grouped; lml and dtheta do not depend on the order, dy is returned in the caller's;
+ * 0: off),
  * "profile_events" (1: per-phase CUDA-event timing, see gpl_last_timing), "poison_ws" (1: the context fills its whole
  * workspace with NaN payloads before every call - a debugging aid: results must not change) */
 int gpl_set_option(gpl_ctx *ctx, const char *key, int value);

@@ -361,16 +361,12 @@ def test_predict_batched_runs_in_passes_beyond_the_workspace_cap(ctx):
 
 
 # ---------------------------------------------------------------------------------------------- structurally zero tiles
-@pytest.mark.parametrize("shuffle", [False, True])
-def test_zero_tile_skipping_keeps_every_bit(shuffle):
+def test_zero_tile_skipping_keeps_every_bit():
     """Block-diagonal covariances (Cat(:subject) * SqExp(:time) on rows grouped by subject: C3) leave most tiles of L exactly
-    zero; the lockstep kernels skip the updates with them and their triangular solves.  Same bits as the dense walk, with
-    grouped rows (tiles are skipped) and with shuffled rows (nothing to skip), lml and gradient."""
+    zero; the lockstep kernels skip the updates with them, their triangular solves and their covariance code.  Same bits as
+    the dense walk - lml, gradient and predictions, including an item with a poisoned length scale and one without noise."""
     d = W.make_c3(features=24)
-    X, Y = d["X"].copy(), d["Y"].copy()
-    if shuffle:
-        perm = np.random.default_rng(0).permutation(X.shape[0])
-        X, Y = X[perm], Y[:, perm]
+    X, Y = d["X"], d["Y"]
     c = _lib.Context(0)
     try:
         prog = c.program(d["ops"])
@@ -392,5 +388,28 @@ def test_zero_tile_skipping_keeps_every_bit(shuffle):
         c.set_option("zero_tile_skip", 0)
         m0, v0, l0, i0 = c.predict_batched(prog, X, Y[0], Theta[:3], 0.0, X[:40] + 0.25)
         assert np.array_equal(m1, m0) and np.array_equal(v1, v0) and np.array_equal(l1, l0)
+    finally:
+        c.close()
+
+
+def test_rows_are_grouped_by_the_shared_category_column():
+    """Rows in any order, option zero_tile_skip = 3: a program whose every term carries Cat on one column has its observations
+    grouped by that column inside the call (lml and dtheta do not depend on the order; dy comes back in the caller's order)."""
+    d = W.make_c3(features=12)
+    perm = np.random.default_rng(0).permutation(d["X"].shape[0])
+    X, Y = d["X"][perm], d["Y"][:, perm]
+    c = _lib.Context(0)
+    try:
+        prog = c.program(d["ops"])
+        c.set_option("zero_tile_skip", 3)
+        lml, info, dth, dy = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        c.set_option("zero_tile_skip", 0)  # no grouping, no flags: the dense walk over the shuffled rows
+        lml0, info0, dth0, dy0 = c.lml_batched(prog, X, Y, d["Theta"], 0.0, grad=True)
+        assert not info.any() and not info0.any()
+        assert np.max(np.abs(lml - lml0) / np.abs(lml0)) < 1e-12
+        assert np.max(np.abs(dth - dth0) / np.maximum(1.0, np.abs(dth0))) < 1e-9
+        assert np.max(np.abs(dy - dy0)) < 1e-9 * max(1.0, np.max(np.abs(dy0)))
+        ref, _ = CO.lml_batched(d["ops"], X, Y, d["Theta"], 0.0)
+        assert np.max(np.abs(lml - ref) / np.abs(ref)) < LML_RTOL
     finally:
         c.close()
