@@ -10,6 +10,9 @@ from gaplac_b200 import _lib, workloads as W  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 d = W.make_c5(n=n)
 ctx = _lib.Context(0)
+for kv in sys.argv[2:]:
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 prog = ctx.program(d["ops"])
 ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
 ctx.set_option("profile_events", 1)
