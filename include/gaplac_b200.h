@@ -106,7 +106,7 @@ uint64_t gpl_launch_count(gpl_ctx *ctx);
  * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path; 2: its one-stream form; 3: look-ahead streams without the worker CTA;
  * 4: the round-1 worker protocol), "trail_int8" (trailing updates of the large-n factorisation on the INT8 tensor path
  * - tcgen05.mma.kind::i8 on 7-bit slices of L, exact INT32 products, FP64 accumulation: -1 (default) automatic = 8 slices,
- * 56 bits below each row's maximum, from n = 8192 on; 0: FP64 DMMA updates at every n; 5..9: that many slices from n = 4096
+ * 56 bits below each row's maximum, from n = 6144 on; 0: FP64 DMMA updates at every n; 5..9: that many slices from n = 4096
  * on - 7 slices keep the lml to ~1e-12, 6 to ~1e-10), "lk_ws_limit_mb" (workspace cap, default 24576),
  * "ou_separable" (default 1: batched log-densities with n > 192 whose program has one or two OU leaves on one column of a
  * shared X sort the observations by that column - the likelihood does not depend on their order; dy is returned in the

@@ -57,8 +57,8 @@ def test_fewer_slices_stay_inside_the_lml_tolerance(own_ctx, slices, tol):
     assert got[2] == 0 and abs(got[0] - base[0]) < tol * abs(base[0])
 
 
-def test_automatic_mode_switches_at_8192_and_reports_the_same_answer(own_ctx):
-    """Default option value: DMMA below n = 8192 (bitwise the round-2 path), the INT8 path from there on."""
+def test_automatic_mode_switches_to_int8_for_large_n_and_reports_the_same_answer(own_ctx):
+    """Default option value: DMMA below n = 6144 (bitwise the DMMA path), the INT8 path from there on."""
     ctx = own_ctx
     d = W.make_c5(n=4096)
     prog = ctx.program(d["ops"])
