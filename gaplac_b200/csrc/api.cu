@@ -57,7 +57,7 @@ struct gpl_ctx {
     bool attr_lml = false, attr_big = false, attr_pred = false, attr_lk = false, attr_post = false;
     size_t lk_ws_limit = (size_t)24 << 30;  // lockstep workspace cap in bytes; larger batches run in chunks
     int ou_separable = 1;                   // 1: sort the observations by the OU column and use the separable form (lockstep lml)
-    int trail_int8 = -1;                    // large-n trailing updates: -1 auto (INT8 split path, 8 slices, from n = 6144 on), 0 FP64 DMMA only,
+    int trail_int8 = -1;                    // large-n trailing updates: -1 auto (INT8 split path, 9 slices, from n = 6144 on), 0 FP64 DMMA only,
                                             // 5..9: that many slices from n = 4096 on
     int zero_tile_skip = 1;                 // lockstep factorisation: skip updates with / solves of exactly-zero tiles: 1 when the program
                                             // can produce them (a Cat factor in every term but the noise), 2 always, 0 never,
@@ -605,7 +605,11 @@ int big_factor(gpl_ctx *ctx, double *tiles, double *winv, double *pivlog, int *d
     static_assert(I8_BLOCK % BIG_PANEL == 0 && I8_BLOCK % 2 == 0, "blocks are whole panels and whole 128-column blocks");
     int i8S = 0;
     if (ctx->trail_int8 > 0 && nt >= 4 * i8_block) i8S = ctx->trail_int8;
-    else if (ctx->trail_int8 < 0 && nt >= 6 * i8_block) i8S = 8;  // measured against DMMA: n = 5120 level, 6144 1.08x, 8192 1.31x, 16384 1.72x
+    else if (ctx->trail_int8 < 0 && nt >= 6 * i8_block) i8S = 9;
+    // 9 slices (63 bits below each row's maximum) match the FP64 path on ill-conditioned covariances as well: SqExp l = 3 +
+    // 1e-6 noise at n = 6144 deviates from LAPACK by 1.5e-10 (DMMA path 2.2e-10); 8 slices give 4.3e-9 there (they are within
+    // 1e-14 of the FP64 path on well-conditioned problems such as C5, and 10-20 % faster: option trail_int8 = 8).
+    // Measured against DMMA with 9 slices: n = 6144 1.02x, 7168 1.11x, 8192 1.19x, 12288 1.36x, 16384 1.42x.
     int *i8dbg = nullptr;
     if (i8S && i8_prepare()) {
         if (ctx->trail_int8 > 0) return fail(ctx, GPL_ERR_CUDA, "INT8 trailing update: kernels or cuTensorMapEncodeTiled unavailable");

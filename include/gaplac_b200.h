@@ -105,9 +105,10 @@ uint64_t gpl_launch_count(gpl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys return GPL_ERR_ARG.  Keys: "lml_variant" (0 lockstep schedule, 1 fused
  * per-item kernel of round 1), "chol_variant" (1: force the multi-CTA large-n path; 2: its one-stream form; 3: look-ahead streams without the worker CTA;
  * 4: the round-1 worker protocol), "trail_int8" (trailing updates of the large-n factorisation on the INT8 tensor path
- * - tcgen05.mma.kind::i8 on 7-bit slices of L, exact INT32 products, FP64 accumulation: -1 (default) automatic = 8 slices,
- * 56 bits below each row's maximum, from n = 6144 on; 0: FP64 DMMA updates at every n; 5..9: that many slices from n = 4096
- * on - 7 slices keep the lml to ~1e-12, 6 to ~1e-10), "lk_ws_limit_mb" (workspace cap, default 24576),
+ * - tcgen05.mma.kind::i8 on 7-bit slices of L, exact INT32 products, FP64 accumulation: -1 (default) automatic = 9 slices,
+ * 63 bits below each row's maximum (as accurate as the FP64 path on ill-conditioned covariances too), from n = 6144 on;
+ * 0: FP64 DMMA updates at every n; 5..9: that many slices from n = 4096 on - on well-conditioned problems 8 slices stay within
+ * 1e-14 of the FP64 path and are 10-20 % faster, 7 slices keep the lml to ~1e-12, 6 to ~1e-10), "lk_ws_limit_mb" (workspace cap, default 24576),
  * "ou_separable" (default 1: batched log-densities with n > 192 whose program has one or two OU leaves on one column of a
  * shared X sort the observations by that column - the likelihood does not depend on their order; dy is returned in the
  * caller's order - and evaluate those leaves in separable form below the diagonal; 0: off; 2: from n > 64 on),

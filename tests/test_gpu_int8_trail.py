@@ -132,3 +132,24 @@ def test_look_ahead_without_the_worker_cta(own_ctx):
     ctx.set_option("trail_int8", 8)
     got = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
     assert got[2] == 0 and abs(got[0] - base[0]) < 1e-12 * abs(base[0])
+
+
+def test_automatic_slice_count_holds_the_tolerance_on_an_ill_conditioned_covariance(own_ctx):
+    """SqExp with l = 3 on 6144 points in (-50, 50) plus 1e-6 noise: condition number ~1e10, FP64 itself is good to ~2e-10 here.
+    The automatic setting (9 slices) stays at that level; 8 slices - 56 bits below the row maxima - lose another digit (4e-9),
+    which is why they are not the default."""
+    ctx = own_ctx
+    d = W.make_c5(n=6144)
+    d["theta"] = np.array([3.0, 1e-6])
+    prog = ctx.program(d["ops"])
+    ref, _ = _lapack_lml(d)
+    auto = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
+    ctx.set_option("trail_int8", 0)
+    dmma = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
+    ctx.set_option("trail_int8", 8)
+    eight = ctx.lml_large(prog, d["X"], d["y"], d["theta"], 0.0)
+    assert auto[2] == 0 and dmma[2] == 0 and eight[2] == 0
+    e_auto, e_dmma, e_eight = (abs(v[0] - ref) / abs(ref) for v in (auto, dmma, eight))
+    assert e_auto < 1e-9 and e_dmma < 1e-9
+    assert e_auto < 3 * e_dmma + 1e-12
+    assert e_eight < 1e-7  # usable, but a digit behind
