@@ -413,3 +413,31 @@ def test_rows_are_grouped_by_the_shared_category_column():
         assert np.max(np.abs(lml - ref) / np.abs(ref)) < LML_RTOL
     finally:
         c.close()
+
+
+def test_zero_tile_flags_next_to_the_separable_ou_sort():
+    """Cat(:subject) * OU(:time) + Noise at n = 300: the program qualifies for the zero-tile flags AND for the separable OU form,
+    whose sort by time interleaves the subjects (few tiles stay zero).  Both mechanisms together: same bits as each alone,
+    oracle tolerance, with and without the gradient."""
+    d = W.make_c3(features=8)
+    ops = [Op(CAT, col=0), Op(OU, col=1, theta_slot=0), Op(MUL), Op(NOISE, var_slot=1), Op(ADD)]
+    Theta = np.column_stack([np.linspace(20, 90, 8), np.linspace(0.1, 0.4, 8)])
+    c = _lib.Context(0)
+    try:
+        prog = c.program(ops)
+        res = {}
+        for skip in (1, 0):
+            for sep in (1, 0):
+                c.set_option("zero_tile_skip", skip)
+                c.set_option("ou_separable", sep)
+                res[(skip, sep)] = c.lml_batched(prog, d["X"], d["Y"], Theta, 0.0, grad=True)
+        for sep in (1, 0):
+            for a, b in zip(res[(1, sep)], res[(0, sep)]):
+                assert np.array_equal(a, b)
+        ref, _ = CO.lml_batched(ops, d["X"], d["Y"], Theta, 0.0)
+        for k, r in res.items():
+            assert not r[1].any()
+            assert np.max(np.abs(r[0] - ref) / np.abs(ref)) < LML_RTOL, k
+        assert np.max(np.abs(res[(1, 1)][2] - res[(0, 0)][2]) / np.maximum(1.0, np.abs(res[(0, 0)][2]))) < 1e-8
+    finally:
+        c.close()
