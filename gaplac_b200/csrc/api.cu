@@ -315,7 +315,10 @@ int launch_lml_lockstep(gpl_ctx *ctx, const DevProgram &prog, int n, int d, cons
     // grouping is opt-in (zero_tile_skip = 3): three extra launches and two permutations per call cost the sampler's small
     // batches 12 % (C3, rows already grouped), so by default the caller's row order is taken as it comes
     if (ctx->zero_tile_skip == 3 && cat_everywhere && group_col >= 0 && allow_sort && !x_batched && n <= 8192 && nt >= 2) sort_col = group_col;
-    else if (ctx->ou_separable && allow_sort && !x_batched && n <= 8192 && (nt >= 4 || (ctx->ou_separable == 2 && nt >= 2))) {
+    // (a program that gets the zero flags keeps the caller's row order - presumably grouped - instead of the OU sort, which
+    // would interleave the groups: skipping most tiles is worth far more than one exponential per entry)
+    else if (!(use_zflags && cat_everywhere) && ctx->ou_separable && allow_sort && !x_batched && n <= 8192 &&
+             (nt >= 4 || (ctx->ou_separable == 2 && nt >= 2))) {
         int cnt = 0;
         for (int f = 0; f < prog.n_factors; ++f)
             if (prog.f[f].kind == F_OU) {
